@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the subpixal hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 10 000 cutout pairs of 64x64 fp32 taken
+from one synthetic 4096x2048 ACS/WFC-like frame (+ the four reference-phase
+frames), cc_type='NCC', full_output=False.  One "step" = one pass of the fused
+gather + cross-correlation + sub-pixel-fit kernel over the 10 000 pairs (per
+GPU; weak scaling), followed for N > 1 by the single NCCL all-gather of the
+shift table.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cutout pairs/sec (CC+subpixel fit)"
+UNIT = "pairs/s"
+FRAME_H, FRAME_W = 2048, 4096
+L2_FLUSH_BYTES = 256 << 20
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
+# kernel, from the committed `ncu --set full` capture (profiles/); None until
+# a capture for the current kernel exists.
+NCU_TRAFFIC_BYTES = {64: None, 128: None, 32: None}
+
+
+def algorithmic_bytes(n):
+    """five NxN fp32 tiles read once, (dx,dy) written."""
+    return 20 * n * n + 8
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (numpy + scipy.signal.fftconvolve +
+# numpy.linalg.lstsq, exactly the libraries the reference calls) on all host
+# cores.  The unmodified reference is Python and lives in /root/reference,
+# which does not exist on the GPU box, hence kind = "port".
+# ----------------------------------------------------------------------------
+_W_STACK = None
+
+
+def _pool_init(path):
+    global _W_STACK
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    import numpy as np
+    _W_STACK = np.load(path, mmap_mode="r")
+
+
+def _pool_work(rng):
+    import warnings
+    import numpy as np
+    from oracle import subpixal_oracle as orc
+    lo, hi = rng
+    out = []
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        for k in range(lo, hi):
+            st = np.asarray(_W_STACK[k])
+            out.append(orc.find_displacement(st[0], st[1], st[2], st[3], st[4], cc_type="NCC"))
+    return out
+
+
+class CpuArm(object):
+    def __init__(self, stack):
+        import multiprocessing as mp
+        import numpy as np
+        self.cores = os.cpu_count() or 1
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        self.path = os.path.join(shm, "spx_bench_sample_%d.npy" % os.getpid())
+        np.save(self.path, stack)
+        self.n = stack.shape[0]
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_pool_init,
+                                                 initargs=(self.path,))
+        self.run(0, min(self.n, 2 * self.cores))          # import + warm caches
+
+    def run(self, lo, hi):
+        """Process pairs [lo, hi) on all cores; returns (seconds, results)."""
+        chunk = max(1, (hi - lo + 4 * self.cores - 1) // (4 * self.cores))
+        tasks = [(a, min(hi, a + chunk)) for a in range(lo, hi, chunk)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_pool_work, tasks)
+        dt = time.perf_counter() - t0
+        return dt, [r for part in res for r in part]
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+
+
+# ----------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def finish(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ----------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from subpixal_b200 import synthetic as syn
+    n = args.size
+    cores = os.cpu_count() or 1
+    per_step = args.ref_pairs_per_core * cores
+    need = min(args.pairs, per_step * 2)
+    sc = syn.make_scene(args.pairs, FRAME_H, FRAME_W, n, seed=args.seed)
+    # render only what the sample needs: the scene restricted to a band of sources
+    # would change the neighbours, so render the full frames once (CPU, torch)
+    frames, _ = syn.make_frames(sc, "cpu")
+    boxes = syn.make_boxes(sc)
+    stack = syn.cut_stack(frames.numpy(), boxes[:need])
+    arm = CpuArm(stack)
+    try:
+        for w in range(args.warmup):
+            arm.run(0, min(need, per_step))
+        total_t, total_n = 0.0, 0
+        for k in range(args.steps):
+            lo = (k % 2) * per_step if need >= 2 * per_step else 0
+            hi = min(need, lo + per_step)
+            dt, _ = arm.run(lo, hi)
+            total_t += dt
+            total_n += hi - lo
+    finally:
+        arm.close()
+    value = total_n / total_t
+    sample = "%d pairs of %dx%d per step on %d cores (multiprocessing pool)" % (
+        min(need, per_step), n, n, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": "%d cutout pairs %dx%d fp32 from one synthetic %dx%d frame "
+                    "(+4 reference-phase frames), cc_type=NCC, full_output=False; "
+                    "per GPU" % (args.pairs, args.size, args.size, FRAME_W, FRAME_H),
+        "pairs_per_gpu": args.pairs, "cutout": args.size, "cc_type": "NCC",
+        "frame": [FRAME_H, FRAME_W], "sharding": "sources sharded by rank, frames per rank",
+        "collective": "1 all_gather of the shift table per step" if world > 1 else "none",
+        "l2": "256 MiB buffer written between timed steps (outside the CUDA-event windows); "
+              "the five frames (168 MB) also exceed the 126 MB L2",
+        "seed": args.seed,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--pairs", type=int, default=10000)
+    ap.add_argument("--seed", type=int, default=20242)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-pairs-per-core", type=int, default=192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+        args.gpus = world
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from subpixal_b200 import batch, dist as sdist, synthetic as syn
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, npairs = args.size, args.pairs
+    sc = syn.make_scene(npairs, FRAME_H, FRAME_W, n, seed=args.seed + rank)
+    frames, truth = syn.make_frames(sc, dev)
+    boxes_np = syn.make_boxes(sc)
+    boxes = torch.from_numpy(boxes_np).to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    _, _, per = sdist.shard_range(npairs * world, rank, world)
+
+    def step_device():
+        sh, pk, st, _ = batch.cc_fit_frames(frames, boxes, n, n, "NCC")
+        if world > 1:
+            return sdist.allgather_results(sdist.pack_results(sh, pk, st, per), npairs * world)
+        return sh, pk, st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    assert bool(torch.isfinite(out[0]).all()), "non-finite shifts in warm-up"
+
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.fill_(1)                      # evict L2 (not inside the event window)
+        a.record()
+        step_device()
+        b.record()
+    barrier()
+    clocks = sampler.finish() if sampler else None
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_total = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    value = world * npairs * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: host buffers in, host results out, every step ---------
+    h_frames = frames.cpu().pin_memory()
+    h_boxes = torch.from_numpy(boxes_np).pin_memory()
+    d_frames = torch.empty_like(frames)
+    d_boxes = torch.empty_like(boxes)
+    h_out = torch.empty((npairs * world if world > 1 else npairs, 2), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        d_frames.copy_(h_frames, non_blocking=True)
+        d_boxes.copy_(h_boxes, non_blocking=True)
+        sh, pk, st, _ = batch.cc_fit_frames(d_frames, d_boxes, n, n, "NCC")
+        if world > 1:
+            sh, pk, st = sdist.allgather_results(sdist.pack_results(sh, pk, st, per), npairs * world)
+        h_out.copy_(sh, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h_out
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * npairs * e2e_steps / (float(e2e_ms.item()) / 1e3)
+    h2d = int(h_frames.numel() * 4 + h_boxes.numel() * 4)
+    d2h = int(h_out.numel() * 8)
+
+    # ---- roofline of the dominant kernel (rank 0's own launches) ----------
+    peak, peak_src = measured_peak()
+    kern_ms = statistics.mean(ms_steps)
+    achieved = npairs * algorithmic_bytes(n) / (kern_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(n),
+                "kernel": "cc_fit_kernel<Cfg%d>" % n, "peak_source": peak_src,
+                "bytes_per_pair": algorithmic_bytes(n), "pairs_per_launch": npairs,
+                "launch_ms": kern_ms,
+                "note": "HBM fraction as BASELINE.json defines it; the kernel is bound by fp32 "
+                        "issue / shared-memory bandwidth (SURVEY.md section 8d), see DESIGN.md"}
+
+    # ---- CPU baseline: the oracle port on this box's host cores (rank 0, N=1) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        want = int(min(npairs, max(4 * cores, 300.0 * cores * args.cpu_seconds)))
+        stack = syn.cut_stack(frames.cpu().numpy(), boxes_np[:want])
+        arm = CpuArm(stack)
+        try:
+            t_probe, _ = arm.run(0, min(want, 8 * cores))
+            rate = min(want, 8 * cores) / t_probe
+            m = int(max(8 * cores, min(want, rate * args.cpu_seconds)))
+            dt, res = arm.run(0, m)
+        finally:
+            arm.close()
+        # the same pairs on the GPU: parity of the benchmarked configuration
+        sh = step_device()[0][:m].cpu().numpy()
+        ref = np.array(res)
+        cpu = {"value": m / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "first %d of the %d pairs (%.1f s wall, multiprocessing pool, "
+                         "oracle = numpy + scipy.signal.fftconvolve + numpy.linalg.lstsq)"
+                         % (m, npairs, dt),
+               "max_abs_shift_diff_vs_gpu_px": float(np.max(np.abs(sh - ref)))}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+/*
+ * subpixal_b200 - C ABI of the B200 (sm_100a) implementation of subpixal's
+ * data-parallel hot path:  cutout gather -> 4-phase cross-correlation ->
+ * interlace -> sub-pixel peak fit.
+ *
+ * The reference (spacetelescope/subpixal) is pure Python and has no FFI of its
+ * own; its boundary for this path is the Python API of three modules
+ * (SURVEY.md section 8b).  Each entry point below states which reference
+ * function(s) it replaces.  The Python package `subpixal_b200` binds these
+ * symbols with ctypes and keeps the reference's signatures on top of them
+ * (see INTEGRATION.md for the stub a subpixal maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     name ends in `_host`; the library never allocates, never synchronises
+ *     the device and never throws: work is enqueued on `stream`
+ *     (a cudaStream_t / CUstream passed as void*; NULL = legacy default).
+ *   - return value: 0 = ok, < 0 = SPX_E_* (bad argument / unsupported size),
+ *     > 0 = a cudaError_t raised while launching.
+ *   - images are row-major, `pitch` counted in ELEMENTS.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef SUBPIXAL_B200_H
+#define SUBPIXAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_ABI_VERSION 1
+
+/* ---- error codes (negative return values) ------------------------------ */
+#define SPX_E_BADARG        (-1)  /* NULL pointer, negative size, bad enum   */
+#define SPX_E_UNSUPPORTED   (-2)  /* cutout larger than SPX_MAX_CUTOUT, ...  */
+#define SPX_E_WORKSPACE     (-3)  /* workspace missing or too small          */
+#define SPX_E_DTYPE         (-4)  /* unsupported element type                */
+
+#define SPX_MAX_CUTOUT 256        /* max ny, nx handled by the CC kernels    */
+#define SPX_MIN_CUTOUT 3          /* 2n >= 6 so the 5x5 fit box exists       */
+
+/* ---- cc_type (cc.py:107-111; anything else behaves as CC, cc.py:108) ---- */
+#define SPX_CC   0
+#define SPX_NCC  1
+#define SPX_ZNCC 2
+
+/* ---- flags -------------------------------------------------------------- */
+#define SPX_F_ZERO_BAD_PHASES 0x1u /* fused path: non-finite pixels of the four
+                                      phase frames are treated as masked and
+                                      set to 0 (align.py:661 + cutout.py:755) */
+#define SPX_F_ZERO_BAD_REF    0x2u /* same for the image ("ref_image") frame;
+                                      NOT reference behaviour, off by default */
+
+/* ---- per-pair status bits (int32 output) --------------------------------
+ * The reference expresses these situations through NaNs and through the
+ * fall-back return values of centroid.find_peak; the bits let the Python
+ * wrapper reproduce them exactly. */
+#define SPX_S_NONFINITE_REF   0x001 /* NaN/Inf in ref_image -> ICC all NaN    */
+#define SPX_S_NONFINITE_P00   0x002 /* NaN/Inf in image00 -> that lattice NaN */
+#define SPX_S_NONFINITE_P10   0x004
+#define SPX_S_NONFINITE_P01   0x008
+#define SPX_S_NONFINITE_P11   0x010
+#define SPX_S_BAD_NORM        0x020 /* std is 0/NaN (cc.py:139-142) -> NaN ICC */
+#define SPX_S_PEAK_EDGE       0x040 /* centroid.py:171-172 integer position   */
+#define SPX_S_NO_MAXIMUM      0x080 /* centroid.py:217-225 box centre         */
+#define SPX_S_FIT_OUTSIDE     0x100 /* centroid.py:230-236 integer position   */
+#define SPX_S_FIT_NONFINITE   0x200 /* NaN in fit box -> integer position     */
+#define SPX_S_BOX_MISMATCH    0x400 /* fused path: box size != (ny, nx)       */
+#define SPX_S_FEW_POINTS      0x800 /* < 6 usable points (centroid.py:160,186,202) */
+#define SPX_S_SINGULAR       0x1000 /* rank-deficient masked fit (find_peak only) */
+
+/* ---- element kinds for the gather --------------------------------------- */
+#define SPX_T_F32 0
+#define SPX_T_F64 1
+#define SPX_T_I8  2   /* integers: only the byte width matters */
+#define SPX_T_I16 3
+#define SPX_T_I32 4
+#define SPX_T_I64 5
+
+int spx_abi_version(void);
+const char *spx_error_string(int code);
+
+/* ========================================================================
+ * (1) Batched cutout gather.
+ * Replaces the crop/mask arithmetic of cutout.Cutout.__init__
+ * (cutout.py:689-797) and the mask updates of the list builders
+ * (cutout.py:188-196, 286-292, 416-427) and, with `zero_masked`, the
+ * sentinel write of align.py:661 - for n boxes in one launch.
+ *
+ * boxes      [n,4] int32 (x1, y1, x2, y2), trc INCLUSIVE (cutout.py:1024-1031);
+ *            boxes may stick out of the frame ('fill' mode); the caller
+ *            rejects 'strict' violations / empty overlaps on the host.
+ * out_offset [n] int64: element offset of cutout k in every output buffer
+ *            (ragged packing; k*h*w for uniform boxes).
+ * data_out   frame dtype; pixels outside the frame get `fillval`.
+ * mask_out   uint8, 1 = bad: outside frame | non-finite | seg != src_id |
+ *            (dq & ~dq_good_bits) != 0.
+ * dq/weight/seg and their outputs may be NULL.  dq_use_bits = 0 skips the
+ * DQ test (dqbitmask=None).  seg test is skipped when src_ids is NULL.
+ * ======================================================================== */
+typedef struct spx_gather_args {
+    const void *frame;      int frame_kind;   /* SPX_T_F32 / SPX_T_F64       */
+    int frame_h, frame_w;   int64_t frame_pitch;
+    const void *dq;         int dq_kind;      /* SPX_T_I8..I64, same shape   */
+    const void *weight;     int weight_kind;  /* SPX_T_F32 / SPX_T_F64       */
+    const void *seg;        int seg_kind;     /* SPX_T_I32 / SPX_T_I64       */
+    const int64_t *src_ids;                   /* [n] or NULL                 */
+    int dq_use_bits;        int64_t dq_good_bits;
+    const int32_t *boxes;   const int64_t *out_offset;   int n;
+    int max_h, max_w;                         /* upper bounds of box sizes   */
+    double fillval;         int zero_masked;
+    void *data_out;  uint8_t *mask_out;  void *dq_out;  void *weight_out;
+} spx_gather_args;
+
+int spx_gather_cutouts(const spx_gather_args *args_host, void *stream);
+
+/* ========================================================================
+ * (2) Batched cross-correlation + sub-pixel fit on cutout stacks.
+ * Replaces cc.find_displacement / _build_icc_image / _normalize
+ * (cc.py:21-156) and the centroid.find_peak call at cc.py:86 for n
+ * independent problems.
+ *
+ * ref, im00, im10, im01, im11: float32 [n][ny][nx] with the given strides
+ *            (elements) between consecutive pairs - a [n,5,ny,nx] stack is
+ *            ref=base, im00=base+ny*nx, ..., stride=5*ny*nx.
+ * shifts     [n,2] float64 (dx, dy)      (cc.py:92-93)
+ * peak       [n] int32 flat argmax index into the (2ny, 2nx) surface
+ * status     [n] int32 SPX_S_* bits
+ * icc        [n,2ny,2nx] float32 or NULL (full_output, cc.py:95,128)
+ * workspace  spx_cc_workspace_bytes(...) bytes, 256-byte aligned
+ * ======================================================================== */
+size_t spx_cc_workspace_bytes(int n, int ny, int nx, int want_icc);
+
+int spx_cc_fit_stack(const float *ref, const float *im00, const float *im10,
+                     const float *im01, const float *im11,
+                     const int64_t pair_stride_host[5],
+                     int n, int ny, int nx, int cc_type,
+                     double *shifts, int32_t *peak, int32_t *status,
+                     float *icc, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ========================================================================
+ * (3) Fused gather + cross-correlation + fit straight from full frames.
+ * = (1) with fillval 0 for five frames sharing one box table, feeding (2)
+ * without the cutouts ever being written to HBM.  frames_host[0] is the
+ * image frame (ref_image), [1..4] the reference frames rendered at the four
+ * half-pixel phases (image00, image10, image01, image11).
+ * boxes [n,4] int32 (x1,y1,x2,y2) must all be nx wide and ny high.
+ * ======================================================================== */
+int spx_cc_fit_frames(const float *const frames_host[5],
+                      int frame_h, int frame_w, int64_t frame_pitch,
+                      const int32_t *boxes, int n, int ny, int nx,
+                      int cc_type, unsigned flags,
+                      double *shifts, int32_t *peak, int32_t *status,
+                      float *icc, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
+/* ========================================================================
+ * (4) Batched centroid.find_peak (centroid.py:18-236) on n surfaces.
+ * surfaces   [n][h][w] float32 or float64 (kind), contiguous.
+ * mask       [n][h][w] uint8, 1 = GOOD (find_peak's convention), or NULL.
+ * guess      [n,2] float64 (xmax, ymax) or NULL (global argmax).
+ * search_wx/wy: brute-force search box around the guess; 0 = no search
+ *            (ignored when guess is NULL - centroid.py:111-127).
+ * fit_wx/wy  peak_fit_box (<= SPX_MAX_FIT_BOX each).
+ * xy         [n,2] float64; status [n] int32; peak [n] int32 flat index of
+ *            the pre-fit pixel.
+ * The auto_expand_search recursion of centroid.py:210-234 is left to the
+ * caller: it re-invokes with guess=NULL for the surfaces whose status has
+ * NO_MAXIMUM / FIT_OUTSIDE set.
+ * ======================================================================== */
+#define SPX_MAX_FIT_BOX 15
+
+int spx_find_peak(const void *surfaces, int kind, int n, int h, int w,
+                  const uint8_t *mask, const double *guess,
+                  int search_wx, int search_wy, int fit_wx, int fit_wy,
+                  double *xy, int32_t *peak, int32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBPIXAL_B200_H */

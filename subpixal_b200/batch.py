@@ -1,0 +1,242 @@
+"""Batched, tensor-level entry points over the C-ABI (the throughput path).
+
+All inputs and outputs are ``torch`` tensors on a CUDA device; the calls only
+enqueue work on the current stream.  These are what the reference-signature
+wrappers in ``cc.py`` / ``centroid.py`` / ``cutout.py`` and ``dist.py`` use.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_CC_TYPES = {"CC": L.CC, "NCC": L.NCC, "ZNCC": L.ZNCC}
+_workspaces = {}
+
+_KIND = {torch.float32: L.T_F32, torch.float64: L.T_F64, torch.int8: L.T_I8,
+         torch.uint8: L.T_I8, torch.int16: L.T_I16, torch.int32: L.T_I32,
+         torch.int64: L.T_I64}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("subpixal_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+
+
+def cc_type_code(cc_type):
+    """cc.py:107-108: case-insensitive; anything unknown behaves as 'CC'."""
+    return _CC_TYPES.get(str(cc_type).upper(), L.CC)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise ValueError(name + " must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise TypeError(name + " must be float32")
+    return t.contiguous()
+
+
+def _outputs(n, ny, nx, want_icc, device):
+    shifts = torch.empty((n, 2), dtype=torch.float64, device=device)
+    peak = torch.empty((n,), dtype=torch.int32, device=device)
+    status = torch.empty((n,), dtype=torch.int32, device=device)
+    icc = (torch.empty((n, 2 * ny, 2 * nx), dtype=torch.float32, device=device)
+           if want_icc else None)
+    return shifts, peak, status, icc
+
+
+def cc_fit_stack(stack, cc_type="NCC", want_icc=False):
+    """Cross-correlate + fit n pairs stored as a ``[n, 5, ny, nx]`` float32
+    stack (slot 0 = ref_image, 1..4 = image00, image10, image01, image11).
+    Returns ``(shifts [n,2] f64, peak [n] i32, status [n] i32, icc or None)``.
+    Batched form of cc.find_displacement (reference cc.py:21-95)."""
+    require_cuda()
+    lib = L.load()
+    stack = _f32c(stack, "stack")
+    if stack.dim() != 4 or stack.shape[1] != 5:
+        raise ValueError("stack must have shape [n, 5, ny, nx]")
+    n, _, ny, nx = (int(v) for v in stack.shape)
+    dev = stack.device
+    with torch.cuda.device(dev):
+        shifts, peak, status, icc = _outputs(n, ny, nx, want_icc, dev)
+        if n == 0:
+            return shifts, peak, status, icc
+        nb = lib.spx_cc_workspace_bytes(n, ny, nx, int(want_icc))
+        ws = _workspace(nb, dev)
+        tile = ny * nx
+        base = stack.data_ptr()
+        strides = (C.c_int64 * 5)(*([5 * tile] * 5))
+        L.check(lib.spx_cc_fit_stack(
+            *(C.c_void_p(base + 4 * tile * s) for s in range(5)), C.byref(strides),
+            n, ny, nx, cc_type_code(cc_type), _ptr(shifts), _ptr(peak), _ptr(status),
+            _ptr(icc), _ptr(ws), ws.numel(), _stream()))
+    return shifts, peak, status, icc
+
+
+def cc_fit_frames(frames, boxes, ny, nx, cc_type="NCC", want_icc=False,
+                  zero_bad_phases=True, zero_bad_ref=False):
+    """Fused gather + cross-correlation + fit straight from five full frames
+    (``frames[0]`` = image frame, ``frames[1..4]`` = reference frames at the
+    four half-pixel phases; a ``[5, H, W]`` tensor or a sequence of five
+    ``[H, W]`` tensors) and an int32 ``[n, 4]`` box table (x1, y1, x2, y2),
+    trc inclusive, every box nx wide and ny high."""
+    require_cuda()
+    lib = L.load()
+    fr = [_f32c(f, "frame") for f in frames]
+    if len(fr) != 5 or any(f.dim() != 2 or f.shape != fr[0].shape for f in fr):
+        raise ValueError("need five [H, W] frames of identical shape")
+    H, W = (int(v) for v in fr[0].shape)
+    dev = fr[0].device
+    boxes = boxes.to(device=dev, dtype=torch.int32).contiguous()
+    if boxes.dim() != 2 or boxes.shape[1] != 4:
+        raise ValueError("boxes must have shape [n, 4]")
+    n = int(boxes.shape[0])
+    flags = (L.F_ZERO_BAD_PHASES if zero_bad_phases else 0) | \
+            (L.F_ZERO_BAD_REF if zero_bad_ref else 0)
+    with torch.cuda.device(dev):
+        shifts, peak, status, icc = _outputs(n, ny, nx, want_icc, dev)
+        if n == 0:
+            return shifts, peak, status, icc
+        nb = lib.spx_cc_workspace_bytes(n, ny, nx, int(want_icc))
+        ws = _workspace(nb, dev)
+        ptrs = (C.c_void_p * 5)(*(f.data_ptr() for f in fr))
+        L.check(lib.spx_cc_fit_frames(
+            C.byref(ptrs), H, W, W, _ptr(boxes), n, int(ny), int(nx),
+            cc_type_code(cc_type), flags, _ptr(shifts), _ptr(peak), _ptr(status),
+            _ptr(icc), _ptr(ws), ws.numel(), _stream()))
+    return shifts, peak, status, icc
+
+
+def gather_cutouts(frame, boxes, dq=None, weight=None, seg=None, src_ids=None,
+                   dq_good_bits=None, fillval=0.0, zero_masked=False):
+    """Batched Cutout crop (reference cutout.py:737-779 and the mask updates at
+    cutout.py:188-196, 286-292, 416-427).  ``boxes`` is an int ``[n, 4]`` table
+    (x1, y1, x2, y2), trc inclusive; sizes may differ (ragged).  Returns a dict
+    with flat ``data`` / ``mask`` (/ ``dq`` / ``weight``) tensors, the int64
+    ``offsets`` ``[n+1]`` and ``shapes`` ``[n, 2]`` (h, w) (CPU tensors)."""
+    require_cuda()
+    lib = L.load()
+    if not frame.is_cuda or frame.dim() != 2:
+        raise ValueError("frame must be a 2-D CUDA tensor")
+    if frame.dtype not in (torch.float32, torch.float64):
+        raise TypeError("frame dtype %s is not supported (float32/float64)" % frame.dtype)
+    if frame.stride(1) != 1:
+        frame = frame.contiguous()
+    dev = frame.device
+    H, W = (int(v) for v in frame.shape)
+    bx = torch.as_tensor(boxes).to(dtype=torch.int64, device="cpu").reshape(-1, 4)
+    n = int(bx.shape[0])
+    hw = torch.stack([bx[:, 3] - bx[:, 1] + 1, bx[:, 2] - bx[:, 0] + 1], dim=1)
+    if n and int(hw.min()) < 1:
+        raise ValueError("Ill-formed extraction box")
+    sizes = hw[:, 0] * hw[:, 1]
+    offsets = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(sizes, 0, out=offsets[1:])
+    total = int(offsets[-1])
+
+    def aux(t, name, kinds):
+        if t is None:
+            return None
+        if not t.is_cuda or tuple(t.shape) != (H, W):
+            raise ValueError("Image's %s array shape must match the shape of image 'data'." % name)
+        if t.dtype not in kinds:
+            raise TypeError("%s dtype %s is not supported" % (name, t.dtype))
+        return t.contiguous()
+
+    ints = (torch.int8, torch.uint8, torch.int16, torch.int32, torch.int64)
+    dq = aux(dq, "DQ", ints)
+    weight = aux(weight, "weight", (torch.float32, torch.float64))
+    seg = aux(seg, "segmentation", (torch.int32, torch.int64))
+    with torch.cuda.device(dev):
+        out = {
+            "data": torch.empty(total, dtype=frame.dtype, device=dev),
+            "mask": torch.empty(total, dtype=torch.uint8, device=dev),
+            "dq": torch.empty(total, dtype=dq.dtype, device=dev) if dq is not None else None,
+            "weight": (torch.empty(total, dtype=weight.dtype, device=dev)
+                       if weight is not None else None),
+            "offsets": offsets, "shapes": hw,
+        }
+        if n == 0:
+            return out
+        d_boxes = bx.to(torch.int32).to(dev)
+        d_off = offsets[:-1].contiguous().to(dev)
+        d_ids = (torch.as_tensor(src_ids).to(dtype=torch.int64).reshape(-1).to(dev)
+                 if (seg is not None and src_ids is not None) else None)
+        if d_ids is not None and d_ids.numel() != n:
+            raise ValueError("src_ids must have one entry per box")
+        a = L.GatherArgs()
+        a.frame, a.frame_kind = frame.data_ptr(), _KIND[frame.dtype]
+        a.frame_h, a.frame_w, a.frame_pitch = H, W, int(frame.stride(0))
+        if dq is not None:
+            a.dq, a.dq_kind = dq.data_ptr(), _KIND[dq.dtype]
+            a.dq_out = out["dq"].data_ptr()
+        if weight is not None:
+            a.weight, a.weight_kind = weight.data_ptr(), _KIND[weight.dtype]
+            a.weight_out = out["weight"].data_ptr()
+        if seg is not None:
+            a.seg, a.seg_kind = seg.data_ptr(), _KIND[seg.dtype]
+        if d_ids is not None:
+            a.src_ids = d_ids.data_ptr()
+        a.dq_use_bits = int(dq is not None and dq_good_bits is not None)
+        a.dq_good_bits = int(dq_good_bits) if dq_good_bits is not None else 0
+        a.boxes, a.out_offset, a.n = d_boxes.data_ptr(), d_off.data_ptr(), n
+        a.max_h, a.max_w = int(hw[:, 0].max()), int(hw[:, 1].max())
+        a.fillval, a.zero_masked = float(fillval), int(bool(zero_masked))
+        a.data_out, a.mask_out = out["data"].data_ptr(), out["mask"].data_ptr()
+        L.check(lib.spx_gather_cutouts(C.byref(a), _stream()))
+        # keep the argument tensors alive until the stream has consumed them
+        out["_keep"] = (d_boxes, d_off, d_ids)
+    return out
+
+
+def find_peak_batch(surfaces, mask=None, guess=None, search_box=(0, 0),
+                    fit_box=(5, 5)):
+    """Batched centroid.find_peak (reference centroid.py:18-236) on a
+    ``[n, h, w]`` float32/float64 CUDA tensor.  ``mask`` (uint8/bool, 1 = good),
+    ``guess`` ``[n, 2]`` float64 (xmax, ymax) or None.  Returns
+    ``(xy [n,2] f64, peak [n] i32, status [n] i32)``."""
+    require_cuda()
+    lib = L.load()
+    if not surfaces.is_cuda or surfaces.dim() != 3:
+        raise ValueError("surfaces must be a [n, h, w] CUDA tensor")
+    if surfaces.dtype not in (torch.float32, torch.float64):
+        raise TypeError("surfaces must be float32 or float64")
+    surfaces = surfaces.contiguous()
+    n, h, w = (int(v) for v in surfaces.shape)
+    dev = surfaces.device
+    if mask is not None:
+        mask = mask.to(device=dev, dtype=torch.uint8).contiguous()
+        if tuple(mask.shape) != (n, h, w):
+            raise ValueError("mask shape must match surfaces")
+    if guess is not None:
+        guess = guess.to(device=dev, dtype=torch.float64).contiguous()
+        if tuple(guess.shape) != (n, 2):
+            raise ValueError("guess must have shape [n, 2]")
+    with torch.cuda.device(dev):
+        xy = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        peak = torch.empty((n,), dtype=torch.int32, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+        if n:
+            L.check(lib.spx_find_peak(
+                _ptr(surfaces), _KIND[surfaces.dtype], n, h, w, _ptr(mask), _ptr(guess),
+                int(search_box[0]), int(search_box[1]), int(fit_box[0]), int(fit_box[1]),
+                _ptr(xy), _ptr(peak), _ptr(status), _stream()))
+    return xy, peak, status

@@ -1,0 +1,66 @@
+"""Build the C-ABI CUDA library in-tree with nvcc for sm_100a.
+
+    python -m subpixal_b200.build            # or __graft_entry__.build()
+
+The shared object is written to ``subpixal_b200/_native/libsubpixal_b200.so``
+(git-ignored, but shipped to the GPU box together with the sources).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+OUT_DIR = os.path.join(PKG_DIR, "_native")
+LIB_PATH = os.path.join(OUT_DIR, "libsubpixal_b200.so")
+SOURCES = ("spx_api.cu", "spx_gather.cu", "spx_peak.cu", "spx_cc.cu")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; cannot build subpixal_b200")
+    return exe
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(os.path.dirname(PKG_DIR), "include", "subpixal_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a and link the shared library."""
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(OUT_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        cmd = [nvcc, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC",
+               "-Xptxas", "-v" if verbose else "-warn-spills",
+               "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
+    link = [nvcc, "-shared", *ARCH, "-o", LIB_PATH, *objs]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s" % (" ".join(link), r.stdout))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

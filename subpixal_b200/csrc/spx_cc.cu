@@ -1,0 +1,299 @@
+// Fused gather + 4-phase cross-correlation + interlace + sub-pixel fit kernel
+// and its C-ABI entry points (2) spx_cc_fit_stack and (3) spx_cc_fit_frames.
+//
+// One persistent CTA processes one cutout pair at a time: the five tiles are
+// read from HBM exactly once per pass over them, every intermediate (spectra,
+// cross-power, correlation rows) lives in shared memory (or, for cutouts too
+// large for one SM, in a per-CTA slab that stays L2 resident), and only the
+// (dx, dy) pair goes back to HBM unless the caller asks for the surface.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/subpixal_b200.h"
+#include "spx_cc_engine.cuh"
+
+namespace spx {
+
+struct CcParams {
+    const float *src[5];        // stack bases or frame bases
+    long long pair_stride[5];   // elements between pairs (0 in frame mode)
+    long long pitch;            // row pitch of every source (elements)
+    int H, W;                   // source image size
+    const int *boxes;           // [n,4] or nullptr (stack mode)
+    int n, ny, nx, cc_type;
+    unsigned flags;
+    double *shifts; int *peak; int *status; float *icc_out;
+    unsigned char *workspace; size_t slab_bytes;
+    size_t off_icc, off_w, off_r;   // byte offsets inside a slab
+};
+
+// ---- configurations (one per supported maximum cutout size) -----------------
+//                P   E1  E2 NMAX   T  MINB  W_SMEM R_SMEM
+using Cfg32  = CcCfg< 48,  6,  8,  32, 128, 4, true,  true >;
+using Cfg64  = CcCfg< 96, 12,  8,  64, 256, 2, true,  true >;
+using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
+using Cfg256 = CcCfg<384, 24, 16, 256, 256, 1, false, false>;
+
+template <class C> struct Layout {
+    // shared memory carve-up (bytes); everything 16-byte aligned
+    static constexpr size_t off_ps = 0;
+    static constexpr size_t off_red = 256;                       // reductions
+    static constexpr size_t red_bytes = 32 * 8 * 8;              // [32 warps][8] doubles
+    static constexpr size_t off_rrow = off_red + red_bytes;
+    static constexpr size_t rrow_bytes = ((C::RH * 2 + 15) / 16) * 16;
+    static constexpr size_t off_S = off_rrow + rrow_bytes;
+    static constexpr size_t off_W = off_S + C::S_ELEMS * 8;
+    static constexpr size_t off_R = off_W + (C::W_SMEM ? C::W_ELEMS * 8 : 0);
+    static constexpr size_t total = off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0);
+    static_assert(sizeof(PairState) <= 256, "PairState must fit its slot");
+};
+
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best t;
+        t.v = __shfl_xor_sync(0xffffffffu, b.v, o);
+        t.idx = __shfl_xor_sync(0xffffffffu, b.idx, o);
+        if (best_better(t, b)) b = t;
+    }
+    return b;
+}
+
+// Execution model of process_pair() on the device: one CTA, block barriers.
+template <class C>
+struct DevExec {
+    double *red;     // [32][8] doubles of reduction scratch in shared memory
+
+    template <class F> __device__ __forceinline__ void par(F f) {
+        f(int(threadIdx.x));
+        __syncthreads();
+    }
+    template <class F> __device__ __forceinline__ void single(F f) {
+        if (threadIdx.x == 0) f();
+        __syncthreads();
+    }
+    template <class F> __device__ __forceinline__ StatPartial reduce_stats(F f) {
+        StatPartial st = f(int(threadIdx.x));
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st.cnt += __shfl_xor_sync(0xffffffffu, st.cnt, o);
+            st.sum += __shfl_xor_sync(0xffffffffu, st.sum, o);
+            st.sq += __shfl_xor_sync(0xffffffffu, st.sq, o);
+            st.rcnt += __shfl_xor_sync(0xffffffffu, st.rcnt, o);
+            st.rsum += __shfl_xor_sync(0xffffffffu, st.rsum, o);
+            st.rsq += __shfl_xor_sync(0xffffffffu, st.rsq, o);
+            st.flags |= __shfl_xor_sync(0xffffffffu, st.flags, o);
+        }
+        if (lane == 0) {
+            double *r = red + warp * 8;
+            r[0] = st.cnt; r[1] = st.sum; r[2] = st.sq;
+            r[3] = st.rcnt; r[4] = st.rsum; r[5] = st.rsq;
+            r[6] = double(st.flags);
+        }
+        __syncthreads();
+        StatPartial tot = stat_zero();
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < C::NW; ++w) {
+                const double *r = red + w * 8;
+                tot.cnt += r[0]; tot.sum += r[1]; tot.sq += r[2];
+                tot.rcnt += r[3]; tot.rsum += r[4]; tot.rsq += r[5];
+                tot.flags |= int(r[6]);
+            }
+        }
+        return tot;
+    }
+    template <class F> __device__ __forceinline__ Best reduce_best(F f) {
+        Best b = warp_best(f(int(threadIdx.x)));
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        float *redf = reinterpret_cast<float *>(red);
+        int *redi = reinterpret_cast<int *>(red) + 64;
+        if (lane == 0) { redf[warp] = b.v; redi[warp] = b.idx; }
+        __syncthreads();
+        Best g = best_init();
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < C::NW; ++w) {
+                Best t; t.v = redf[w]; t.idx = redi[w];
+                if (best_better(t, g)) g = t;
+            }
+        }
+        return g;
+    }
+    __device__ __forceinline__ void or_status(int *p, int v) { atomicOr(p, v); }
+    __device__ __forceinline__ float load_icc(const float *p) { return __ldcg(p); }
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams prm) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    using L = Layout<C>;
+    uint16_t *rrow = reinterpret_cast<uint16_t *>(smem + L::off_rrow);
+    unsigned char *slab = prm.workspace + size_t(blockIdx.x) * prm.slab_bytes;
+
+    Ctx<C> c;
+    c.S = reinterpret_cast<cf *>(smem + L::off_S);
+    c.W = C::W_SMEM ? reinterpret_cast<cf *>(smem + L::off_W)
+                    : reinterpret_cast<cf *>(slab + prm.off_w);
+    c.R = C::R_SMEM ? reinterpret_cast<cf *>(smem + L::off_R)
+                    : reinterpret_cast<cf *>(slab + prm.off_r);
+    c.rrow = rrow;
+    c.ps = reinterpret_cast<PairState *>(smem + L::off_ps);
+
+    DevExec<C> ex;
+    ex.red = reinterpret_cast<double *>(smem + L::off_red);
+
+    if (threadIdx.x == 0) build_rrow<C>(rrow);
+    __syncthreads();
+
+    const size_t icc_elems = size_t(4) * prm.ny * prm.nx;
+    for (int p = blockIdx.x; p < prm.n; p += gridDim.x) {
+        c.icc = prm.icc_out ? prm.icc_out + size_t(p) * icc_elems
+                            : reinterpret_cast<float *>(slab + prm.off_icc);
+        PairJob job;
+        job.x1 = 0; job.y1 = 0; job.status0 = 0;
+        if (prm.boxes) {
+            const int4 b = __ldg(reinterpret_cast<const int4 *>(prm.boxes) + p);
+            job.x1 = b.x; job.y1 = b.y;
+            if (b.z - b.x + 1 != prm.nx || b.w - b.y + 1 != prm.ny)
+                job.status0 = SPX_S_BOX_MISMATCH;
+        }
+        for (int s = 0; s < 5; ++s) job.base[s] = prm.src[s] + size_t(p) * prm.pair_stride[s];
+        job.pitch = prm.pitch; job.H = prm.H; job.W = prm.W;
+        job.ny = prm.ny; job.nx = prm.nx; job.cc_type = prm.cc_type;
+        job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
+        process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
+    }
+}
+
+// ---- host side ------------------------------------------------------------------
+struct SlabPlan { size_t off_icc, off_w, off_r, bytes; int max_ctas_per_sm; };
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <class C>
+static SlabPlan plan_slab(int ny, int nx, bool want_icc) {
+    SlabPlan s;
+    size_t o = 0;
+    s.off_icc = o; if (!want_icc) o += align_up(size_t(16) * ny * nx, 256);
+    s.off_w = o;   if (!C::W_SMEM) o += align_up(C::W_ELEMS * 8, 256);
+    s.off_r = o;   if (!C::R_SMEM) o += align_up(C::R_ELEMS * 8, 256);
+    s.bytes = align_up(o, 256);
+    s.max_ctas_per_sm = C::MINB;
+    return s;
+}
+
+static int num_sms() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+        cudaGetLastError();
+        sms = 148;                       // B200
+    }
+    return sms;
+}
+
+static int pick_cfg(int ny, int nx) {
+    const int m = ny > nx ? ny : nx;
+    if (m <= 32) return 32;
+    if (m <= 64) return 64;
+    if (m <= 128) return 128;
+    if (m <= 256) return 256;
+    return 0;
+}
+
+static SlabPlan plan_for(int cfg, int ny, int nx, bool want_icc) {
+    switch (cfg) {
+        case 32: return plan_slab<Cfg32>(ny, nx, want_icc);
+        case 64: return plan_slab<Cfg64>(ny, nx, want_icc);
+        case 128: return plan_slab<Cfg128>(ny, nx, want_icc);
+        default: return plan_slab<Cfg256>(ny, nx, want_icc);
+    }
+}
+
+static int grid_for(int n, const SlabPlan &sp) {
+    const long long cap = (long long)num_sms() * sp.max_ctas_per_sm;
+    return int(n < cap ? n : cap);
+}
+
+template <class C>
+static int launch(CcParams &prm, const SlabPlan &sp, cudaStream_t stream) {
+    const size_t smem = Layout<C>::total;
+    cudaError_t e = cudaFuncSetAttribute(cc_fit_kernel<C>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return int(e);
+    const int grid = grid_for(prm.n, sp);
+    cc_fit_kernel<C><<<grid, C::T, smem, stream>>>(prm);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : int(e);
+}
+
+static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *stream) {
+    if (prm.n < 0 || !prm.shifts || !prm.peak || !prm.status) return SPX_E_BADARG;
+    for (int s = 0; s < 5; ++s) if (!prm.src[s]) return SPX_E_BADARG;
+    if (prm.ny < SPX_MIN_CUTOUT || prm.nx < SPX_MIN_CUTOUT) return SPX_E_UNSUPPORTED;
+    const int cfg = pick_cfg(prm.ny, prm.nx);
+    if (!cfg) return SPX_E_UNSUPPORTED;
+    if (prm.n == 0) return 0;
+    if (prm.cc_type != SPX_NCC && prm.cc_type != SPX_ZNCC) prm.cc_type = SPX_CC;  // cc.py:108
+    const SlabPlan sp = plan_for(cfg, prm.ny, prm.nx, prm.icc_out != nullptr);
+    const size_t need = sp.bytes * size_t(grid_for(prm.n, sp));
+    if (need > 0 && (!workspace || workspace_bytes < need)) return SPX_E_WORKSPACE;
+    prm.workspace = static_cast<unsigned char *>(workspace);
+    prm.slab_bytes = sp.bytes;
+    prm.off_icc = sp.off_icc; prm.off_w = sp.off_w; prm.off_r = sp.off_r;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (cfg) {
+        case 32: return launch<Cfg32>(prm, sp, st);
+        case 64: return launch<Cfg64>(prm, sp, st);
+        case 128: return launch<Cfg128>(prm, sp, st);
+        default: return launch<Cfg256>(prm, sp, st);
+    }
+}
+
+}  // namespace spx
+
+extern "C" {
+
+size_t spx_cc_workspace_bytes(int n, int ny, int nx, int want_icc) {
+    const int cfg = spx::pick_cfg(ny, nx);
+    if (!cfg || n <= 0 || ny < 1 || nx < 1) return 0;
+    const spx::SlabPlan sp = spx::plan_for(cfg, ny, nx, want_icc != 0);
+    return sp.bytes * size_t(spx::grid_for(n, sp));
+}
+
+int spx_cc_fit_stack(const float *ref, const float *im00, const float *im10,
+                     const float *im01, const float *im11,
+                     const int64_t pair_stride_host[5],
+                     int n, int ny, int nx, int cc_type,
+                     double *shifts, int32_t *peak, int32_t *status,
+                     float *icc, void *workspace, size_t workspace_bytes,
+                     void *stream) {
+    if (!pair_stride_host) return SPX_E_BADARG;
+    spx::CcParams prm{};
+    const float *src[5] = {ref, im00, im10, im01, im11};
+    for (int s = 0; s < 5; ++s) { prm.src[s] = src[s]; prm.pair_stride[s] = pair_stride_host[s]; }
+    prm.pitch = nx; prm.H = ny; prm.W = nx;
+    prm.boxes = nullptr;
+    prm.n = n; prm.ny = ny; prm.nx = nx; prm.cc_type = cc_type; prm.flags = 0;
+    prm.shifts = shifts; prm.peak = peak; prm.status = status; prm.icc_out = icc;
+    return spx::run_cc(prm, workspace, workspace_bytes, stream);
+}
+
+int spx_cc_fit_frames(const float *const frames_host[5],
+                      int frame_h, int frame_w, int64_t frame_pitch,
+                      const int32_t *boxes, int n, int ny, int nx,
+                      int cc_type, unsigned flags,
+                      double *shifts, int32_t *peak, int32_t *status,
+                      float *icc, void *workspace, size_t workspace_bytes,
+                      void *stream) {
+    if (!frames_host || !boxes || frame_h < 1 || frame_w < 1 || frame_pitch < frame_w)
+        return SPX_E_BADARG;
+    spx::CcParams prm{};
+    for (int s = 0; s < 5; ++s) { prm.src[s] = frames_host[s]; prm.pair_stride[s] = 0; }
+    prm.pitch = frame_pitch; prm.H = frame_h; prm.W = frame_w;
+    prm.boxes = boxes;
+    prm.n = n; prm.ny = ny; prm.nx = nx; prm.cc_type = cc_type; prm.flags = flags;
+    prm.shifts = shifts; prm.peak = peak; prm.status = status; prm.icc_out = icc;
+    return spx::run_cc(prm, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,604 @@
+// Cross-correlation engine: the per-thread work of every pass of the fused
+// gather -> normalise -> 4-phase correlation -> interlace -> argmax pipeline.
+//
+// Mathematics (reference cc.py:98-128):
+//   C_ab(ly,lx) = sum_{j,i} ref[j,i] * im_ab[j+ly, i+lx]
+//   ICC[2k+b, 2l+a] = C_ab(k - yc, l - xc),  yc=(ny-1)//2, xc=(nx-1)//2
+// computed as a circular correlation of size P x P, P >= n + max(c, n-1-c)
+// (alias-free for the kept lags), with the image tiles placed at offset
+// (yc, xc) so that output sample m IS lag m - c:
+//   c = IFFT2( conj(FFT2(ref)) * FFT2(im00 + i*im10) )  ->  Re = C_00, Im = C_10
+// (two real phases ride on one complex transform; ref is real so linearity
+// keeps them separate).  The four phase surfaces are written interlaced.
+//
+// Data flow per phase pair (1-D FFT of length P = E1*E2 done as two register
+// codelets with one exchange through memory; columns first so that lanes run
+// along x for the dense input tiles):
+//   C1  tiles -> E1-point FFT down columns (+twiddle)          -> W[P][nx]
+//   C2  E2-point FFT down columns, in place                    -> W (ky scrambled)
+//   for each batch of 32 rows (lanes = rows):
+//     X1  E1-point FFT along x of the nx non-zero samples      -> S[32][P]
+//     X2  E2-point FFT, * conj(R), E2-point inverse FFT        -> S
+//     X3  E1-point inverse FFT, keep the nx wanted lags        -> W[P][nx]
+//   IC1 E2-point inverse FFT down columns (+twiddle), in place -> W
+//   IC2 E1-point inverse FFT, keep ny lags, scale, interlace   -> ICC, argmax
+// The reference image goes through C1, C2, X1 and a final E2-point FFT whose
+// conjugate, times the normalisation scale, is stored as R (half spectrum,
+// ky in [0, P/2], Hermitian symmetry supplies the rest).
+#pragma once
+#include <limits.h>
+#include "spx_common.cuh"
+#include "spx_fft.cuh"
+#include "spx_peak.cuh"
+
+namespace spx {
+
+// --------------------------------------------------------------------------
+// twiddle tables: __constant__ on the device, plain statics for the host emu
+// --------------------------------------------------------------------------
+#ifndef SPX_HOST_EMU
+__constant__ TwTable<48>  c_tw48  = TwTable<48>();
+__constant__ TwTable<96>  c_tw96  = TwTable<96>();
+__constant__ TwTable<192> c_tw192 = TwTable<192>();
+__constant__ TwTable<384> c_tw384 = TwTable<384>();
+#endif
+static const TwTable<48>  h_tw48  = TwTable<48>();
+static const TwTable<96>  h_tw96  = TwTable<96>();
+static const TwTable<192> h_tw192 = TwTable<192>();
+static const TwTable<384> h_tw384 = TwTable<384>();
+
+template <int P> SPX_HD cf tw(int k);
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return cmake(c_tw##P.re[k], c_tw##P.im[k]); }
+#else
+#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return cmake(h_tw##P.re[k], h_tw##P.im[k]); }
+#endif
+SPX_TW(48) SPX_TW(96) SPX_TW(192) SPX_TW(384)
+#undef SPX_TW
+
+// --------------------------------------------------------------------------
+// configuration
+// --------------------------------------------------------------------------
+template <int P_, int E1_, int E2_, int NMAX_, int T_, int MINB_, bool WSM_, bool RSM_>
+struct CcCfg {
+    static constexpr int P = P_, E1 = E1_, E2 = E2_, NMAX = NMAX_, T = T_, MINB = MINB_;
+    static constexpr bool W_SMEM = WSM_, R_SMEM = RSM_;
+    static constexpr int NW = T / 32;
+    static constexpr int WP = NMAX + 1;      // pitch of W (complex), odd
+    static constexpr int SP = P + 1;         // pitch of the row scratch, odd
+    static constexpr int RP = P + 1;         // pitch of R, odd
+    static constexpr int RH = P / 2 + 1;     // rows of R (half spectrum)
+    static constexpr int BATCH = 32;         // rows per row-op batch (= lanes)
+    static constexpr size_t W_ELEMS = size_t(P) * WP;
+    static constexpr size_t S_ELEMS = size_t(BATCH) * SP;
+    static constexpr size_t R_ELEMS = size_t(RH) * RP;
+    static_assert(E1 * E2 == P, "P = E1*E2");
+    static_assert(P % 2 == 0 && NMAX % 2 == 0, "even sizes");
+    static_assert(T % 32 == 0, "whole warps");
+    // alias-free for every n <= NMAX: P >= n + n/2
+    static_assert(P >= NMAX + NMAX / 2, "transform too small");
+};
+
+// Per-pair state, written by thread 0 / the block reductions.
+struct PairState {
+    const float *base[5];
+    long long pitch[5];
+    int y0[5], x0[5];      // cutout origin inside the source image
+    int H, W;              // source image size (ny, nx in stack mode)
+    int ny, nx, yc, xc;
+    int cc_type;
+    unsigned flags;
+    float mu, mu_ref;      // ZNCC means (0 otherwise)
+    float rscale;          // normalisation folded into R
+    int status;
+    Best best;             // running argmax over the interlaced surface
+};
+
+template <class C>
+struct Ctx {
+    cf *W, *S, *R;
+    float *icc;            // [2ny][2nx] interlaced surface of this pair
+    const uint16_t *rrow;  // rows of W (scrambled ky order) with ky <= P/2
+    PairState *ps;
+};
+
+SPX_HD float ld_f32(const float *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// pixel (y, x) of tile s in cutout coordinates, 0 outside the source image
+// (Cutout 'fill' mode with fillval 0, cutout.py:737-752)
+SPX_HD float load_px(const PairState &ps, int s, int y, int x) {
+    const int yy = y + ps.y0[s], xx = x + ps.x0[s];
+    if (yy < 0 || yy >= ps.H || xx < 0 || xx >= ps.W) return 0.f;
+    return ld_f32(ps.base[s] + (long long)yy * ps.pitch[s] + xx);
+}
+
+// W row r holds frequency ky = r/E2 + E1*(r%E2)  (in-place two-step order)
+template <class C> SPX_HD int ky_of_row(int r) { return r / C::E2 + C::E1 * (r % C::E2); }
+
+// --------------------------------------------------------------------------
+// statistics pre-pass (cc.py:131-156), one thread's share
+// --------------------------------------------------------------------------
+struct StatPartial {
+    double cnt, sum, sq, rcnt, rsum, rsq;
+    int flags;
+};
+SPX_HD StatPartial stat_zero() {
+    StatPartial s; s.cnt = s.sum = s.sq = s.rcnt = s.rsum = s.rsq = 0.0; s.flags = 0; return s;
+}
+SPX_HD void stat_merge(StatPartial &a, const StatPartial &b) {
+    a.cnt += b.cnt; a.sum += b.sum; a.sq += b.sq;
+    a.rcnt += b.rcnt; a.rsum += b.rsum; a.rsq += b.rsq; a.flags |= b.flags;
+}
+
+SPX_HD bool zero_bad(const PairState &ps, int s) {
+    return s == 0 ? (ps.flags & SPX_F_ZERO_BAD_REF) != 0
+                  : (ps.flags & SPX_F_ZERO_BAD_PHASES) != 0;
+}
+
+// fetch + sanitise: non-finite pixels become 0; they raise the tile's status
+// bit unless the caller asked for masked-pixel zeroing (align.py:661)
+SPX_HD float fetch(const PairState &ps, int s, int y, int x, int &flags) {
+    float v = load_px(ps, s, y, x);
+    if (!finitef(v)) {
+        if (!zero_bad(ps, s)) flags |= (SPX_S_NONFINITE_REF << s);
+        v = 0.f;
+    }
+    return v;
+}
+
+template <class C>
+SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
+    StatPartial st = stat_zero();
+    const int npix = ps.ny * ps.nx;
+    for (int idx = tid; idx < npix; idx += C::T) {
+        const int y = idx / ps.nx, x = idx - y * ps.nx;
+        bool any = false;
+        for (int s = 1; s < 5; ++s) {
+            const float v = fetch(ps, s, y, x, st.flags);
+            if (v != 0.f) {                               // cc.py:134-137
+                const double d = double(v);
+                st.cnt += 1.0; st.sum += d; st.sq += d * d;
+                any = true;
+            }
+        }
+        const float r = fetch(ps, 0, y, x, st.flags);
+        if (any) {                                        // cc.py:150-154
+            const double d = double(r);
+            st.rcnt += 1.0; st.rsum += d; st.rsq += d * d;
+        }
+    }
+    return st;
+}
+
+SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
+    ps.status |= t.flags;
+    const bool zero = ps.cc_type == SPX_ZNCC;
+    double mu = 0.0, sig = NAN, rmu = 0.0, rsig = NAN;
+    if (t.cnt > 0.0) {
+        mu = t.sum / t.cnt;
+        double var = t.sq / t.cnt - mu * mu;
+        sig = sqrt(var > 0.0 ? var : 0.0);
+    }
+    if (t.rcnt > 0.0) {
+        rmu = t.rsum / t.rcnt;
+        double var = t.rsq / t.rcnt - rmu * rmu;
+        rsig = sqrt(var > 0.0 ? var : 0.0);
+    }
+    const float sf = float(sig), rf = float(rsig);
+    const double sc = 1.0 / (double(sf) * double(rf));
+    ps.mu = zero ? float(mu) : 0.f;
+    ps.mu_ref = zero ? float(rmu) : 0.f;
+    if (!(sc == sc) || !(fabs(sc) < 1e300) || sf == 0.f || rf == 0.f) {
+        ps.status |= SPX_S_BAD_NORM;
+        ps.rscale = 1.f;
+    } else {
+        ps.rscale = float(sc);
+    }
+    if (t.flags) ps.status |= SPX_S_BAD_NORM;   // NaN/Inf poisons the statistics
+}
+
+// --------------------------------------------------------------------------
+// column passes
+// --------------------------------------------------------------------------
+// C1: tiles (sa -> real part, sb -> imaginary part, sb < 0: none) placed at
+// row offset yoff; E1-point FFT over n1 for every (column i, n2).
+template <class C>
+SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
+    const PairState &ps = *c.ps;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchunk = (ps.nx + 31) >> 5;
+    const bool is_ref = (sa == 0);
+    int flags = 0;
+    for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
+        const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
+        const bool active = i < ps.nx;
+        cf x[C::E1];
+        static_for<0, C::E1>([&](auto N1) {
+            constexpr int n1 = decltype(N1)::value;
+            const int y = C::E2 * n1 + n2 - yoff;
+            float va = 0.f, vb = 0.f;
+            if (active && y >= 0 && y < ps.ny) {
+                va = fetch(ps, sa, y, i, flags);
+                if (is_ref) va -= ps.mu_ref;                  // cc.py:152-153
+                else if (va != 0.f) va -= ps.mu;              // cc.py:145-146
+                if (sb >= 0) {
+                    vb = fetch(ps, sb, y, i, flags);
+                    if (vb != 0.f) vb -= ps.mu;
+                }
+            }
+            x[n1] = cmake(va, vb);
+        });
+        RegFFT<C::E1, false>::run(x);
+        if (active) {
+            static_for<0, C::E1>([&](auto K1) {
+                constexpr int k1 = decltype(K1)::value;
+                c.W[(k1 * C::E2 + n2) * C::WP + i] = cmul(x[k1], tw<C::P>(n2 * k1));
+            });
+        }
+    }
+    return flags;
+}
+
+// C2: E2-point FFT over n2 for every (column, k1), in place.
+template <class C>
+SPX_HD void c2_pass(const Ctx<C> &c, int tid) {
+    const PairState &ps = *c.ps;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchunk = (ps.nx + 31) >> 5;
+    for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
+        const int k1 = wi % C::E1, i = (wi / C::E1) * 32 + lane;
+        if (i >= ps.nx) continue;
+        cf x[C::E2];
+        static_for<0, C::E2>([&](auto N2) {
+            constexpr int n2 = decltype(N2)::value;
+            x[n2] = c.W[(k1 * C::E2 + n2) * C::WP + i];
+        });
+        RegFFT<C::E2, false>::run(x);
+        static_for<0, C::E2>([&](auto K2) {
+            constexpr int k2 = decltype(K2)::value;
+            c.W[(k1 * C::E2 + k2) * C::WP + i] = x[k2];
+        });
+    }
+}
+
+// IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
+template <class C>
+SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
+    const PairState &ps = *c.ps;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchunk = (ps.nx + 31) >> 5;
+    for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
+        const int k1 = wi % C::E1, l = (wi / C::E1) * 32 + lane;
+        if (l >= ps.nx) continue;
+        cf x[C::E2];
+        static_for<0, C::E2>([&](auto K2) {
+            constexpr int k2 = decltype(K2)::value;
+            x[k2] = c.W[(k1 * C::E2 + k2) * C::WP + l];
+        });
+        RegFFT<C::E2, true>::run(x);
+        static_for<0, C::E2>([&](auto N2) {
+            constexpr int n2 = decltype(N2)::value;
+            c.W[(k1 * C::E2 + n2) * C::WP + l] = cmulc(x[n2], tw<C::P>(n2 * k1));
+        });
+    }
+}
+
+// IC2: E1-point inverse FFT over k1; outputs n = E2*n1+n2 < ny are the lags
+// n - yc of phases (a=0, b) [real part] and (a=1, b) [imaginary part].
+template <class C>
+SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
+    const PairState &ps = *c.ps;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nchunk = (ps.nx + 31) >> 5;
+    const float norm = 1.0f / (float(C::P) * float(C::P));
+    const int w2 = 2 * ps.nx;
+    Best best = best_init();
+    for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
+        const int n2 = wi % C::E2, l = (wi / C::E2) * 32 + lane;
+        if (l >= ps.nx) continue;
+        cf x[C::E1];
+        static_for<0, C::E1>([&](auto K1) {
+            constexpr int k1 = decltype(K1)::value;
+            x[k1] = c.W[(k1 * C::E2 + n2) * C::WP + l];
+        });
+        RegFFT<C::E1, true>::run(x);
+        static_for<0, C::E1>([&](auto N1) {
+            constexpr int n1 = decltype(N1)::value;
+            const int n = C::E2 * n1 + n2;
+            if (n < ps.ny) {
+                const float v0 = x[n1].x * norm, v1 = x[n1].y * norm;
+                const int idx = (2 * n + b) * w2 + 2 * l;
+                cf o = cmake(v0, v1);
+                *reinterpret_cast<cf *>(c.icc + idx) = o;
+                Best c0; c0.v = v0; c0.idx = idx;
+                Best c1; c1.v = v1; c1.idx = idx + 1;
+                if (best_better(c0, best)) best = c0;
+                if (best_better(c1, best)) best = c1;
+            }
+        });
+    }
+    return best;
+}
+
+// --------------------------------------------------------------------------
+// row passes on one batch of 32 rows; lane <-> row
+// --------------------------------------------------------------------------
+// X1: r = W row handled by this lane (or -1), xoff = column offset of the tile
+template <class C>
+SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
+    const PairState &ps = *c.ps;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
+        cf x[C::E1];
+        static_for<0, C::E1>([&](auto N1) {
+            constexpr int n1 = decltype(N1)::value;
+            const int i = C::E2 * n1 + n2 - xoff;
+            x[n1] = (r >= 0 && i >= 0 && i < ps.nx) ? c.W[r * C::WP + i] : cmake(0.f, 0.f);
+        });
+        RegFFT<C::E1, false>::run(x);
+        static_for<0, C::E1>([&](auto K1) {
+            constexpr int k1 = decltype(K1)::value;
+            c.S[lane * C::SP + k1 * C::E2 + n2] = cmul(x[k1], tw<C::P>(n2 * k1));
+        });
+    }
+}
+
+// X2 for the reference image: finish the forward transform and store
+// conj(R) * rscale for ky <= P/2.
+template <class C>
+SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int ky) {
+    const PairState &ps = *c.ps;
+    const int warp = tid >> 5, lane = tid & 31;
+    const float sc = ps.rscale;
+    for (int k1 = warp; k1 < C::E1; k1 += C::NW) {
+        cf x[C::E2];
+        static_for<0, C::E2>([&](auto N2) {
+            constexpr int n2 = decltype(N2)::value;
+            x[n2] = c.S[lane * C::SP + k1 * C::E2 + n2];
+        });
+        RegFFT<C::E2, false>::run(x);
+        if (ky >= 0) {
+            static_for<0, C::E2>([&](auto K2) {
+                constexpr int k2 = decltype(K2)::value;
+                c.R[ky * C::RP + k1 * C::E2 + k2] = cmake(x[k2].x * sc, -x[k2].y * sc);
+            });
+        }
+    }
+}
+
+// X2: forward E2-FFT, multiply by conj(R[ky, kx]), inverse E2-FFT (+twiddle)
+template <class C>
+SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ky = r >= 0 ? ky_of_row<C>(r) : 0;
+    const bool flip = ky > C::P / 2;
+    const cf *Rrow = c.R + (flip ? C::P - ky : ky) * C::RP;
+    for (int k1 = warp; k1 < C::E1; k1 += C::NW) {
+        cf x[C::E2];
+        static_for<0, C::E2>([&](auto N2) {
+            constexpr int n2 = decltype(N2)::value;
+            x[n2] = c.S[lane * C::SP + k1 * C::E2 + n2];
+        });
+        RegFFT<C::E2, false>::run(x);
+        static_for<0, C::E2>([&](auto K2) {
+            constexpr int k2 = decltype(K2)::value;
+            const int kx = k1 + C::E1 * k2;                 // warp-uniform
+            const int kxm = (C::P - kx) % C::P;
+            const int col_d = k1 * C::E2 + k2;
+            const int col_f = (kxm % C::E1) * C::E2 + kxm / C::E1;
+            cf v = Rrow[flip ? col_f : col_d];
+            if (flip) v.y = -v.y;   // conj(R[ky,kx]) = R[P-ky,P-kx]; storage holds conj(R)
+            x[k2] = cmul(x[k2], v);
+        });
+        RegFFT<C::E2, true>::run(x);
+        static_for<0, C::E2>([&](auto N2) {
+            constexpr int n2 = decltype(N2)::value;
+            c.S[lane * C::SP + k1 * C::E2 + n2] = cmulc(x[n2], tw<C::P>(n2 * k1));
+        });
+    }
+}
+
+// X3: E1-point inverse FFT over k1, keep samples m = E2*n1+n2 < nx
+template <class C>
+SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r) {
+    const PairState &ps = *c.ps;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
+        cf x[C::E1];
+        static_for<0, C::E1>([&](auto K1) {
+            constexpr int k1 = decltype(K1)::value;
+            x[k1] = c.S[lane * C::SP + k1 * C::E2 + n2];
+        });
+        RegFFT<C::E1, true>::run(x);
+        if (r >= 0) {
+            static_for<0, C::E1>([&](auto N1) {
+                constexpr int n1 = decltype(N1)::value;
+                const int m = C::E2 * n1 + n2;
+                if (m < ps.nx) c.W[r * C::WP + m] = x[n1];
+            });
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// peak stage (one thread): numpy.argmax semantics incl. NaN lattices, then
+// centroid.find_peak with peak_fit_box=5 (cc.py:86) and cc.py:89-93.
+// --------------------------------------------------------------------------
+template <class LoadF>
+SPX_HD void peak_stage(const PairState &ps, Best best, LoadF ldicc,
+                       double *shift2, int *peak, int *status) {
+    const int h2 = 2 * ps.ny, w2 = 2 * ps.nx;
+    int st = ps.status;
+    int idx = best.idx;
+    const bool norm = ps.cc_type != SPX_CC;
+    const int nf_all = SPX_S_NONFINITE_REF | SPX_S_BAD_NORM;
+    const int nf_ph = SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
+                      SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
+    bool nanfit = false;
+    if ((st & nf_all) || (norm && (st & nf_ph))) {
+        idx = 0; nanfit = true;                 // whole surface NaN
+    } else if (st & nf_ph) {                    // CC: first NaN lattice, row-major
+        idx = (st & SPX_S_NONFINITE_P00) ? 0 : (st & SPX_S_NONFINITE_P10) ? 1
+            : (st & SPX_S_NONFINITE_P01) ? w2 : w2 + 1;
+        nanfit = true;
+    }
+    const int jmax = idx / w2, imax = idx - jmax * w2;
+    PeakOut po;
+    if (nanfit) {
+        // every 5x5 box around a NaN peak contains NaN -> find_peak returns the
+        // integer position (edge rule or NaN-coefficient fall-through)
+        po.x = double(imax); po.y = double(jmax);
+        po.status = (imax == 0 || jmax == 0) ? SPX_S_PEAK_EDGE : SPX_S_FIT_NONFINITE;
+    } else {
+        po = fit_peak([&](int j, int i) { return double(ldicc(j * w2 + i)); },
+                      [](int, int) { return true; }, h2, w2, imax, jmax,
+                      double(imax), double(jmax), 5, 5);
+    }
+    st |= po.status;
+    const int xc4 = (w2 - 1) / 4, yc4 = (h2 - 1) / 4;            // cc.py:89-90
+    shift2[0] = 0.5 * po.x - double(xc4);                         // cc.py:92-93
+    shift2[1] = 0.5 * po.y - double(yc4);
+    *peak = idx;
+    *status = st;
+}
+
+// value the reference's surface has at flat index idx when inputs were
+// non-finite / the normalisation failed (used to patch a requested ICC)
+SPX_HD bool icc_is_nan(const PairState &ps, int status, int idx) {
+    const int w2 = 2 * ps.nx;
+    const int j = idx / w2, i = idx - j * w2;
+    const int lattice = (j & 1) * 2 + (i & 1);         // 0:00 1:10 2:01 3:11
+    const bool norm = ps.cc_type != SPX_CC;
+    const int nf_ph = SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
+                      SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
+    if (status & (SPX_S_NONFINITE_REF | SPX_S_BAD_NORM)) return true;
+    if (norm && (status & nf_ph)) return true;
+    return (status & (SPX_S_NONFINITE_P00 << lattice)) != 0;
+}
+
+// --------------------------------------------------------------------------
+// The pass sequence for ONE pair.  `Ex` supplies the execution model:
+//   par(f)          run f(tid) for every thread of the CTA, then barrier
+//   single(f)       run f() on one thread, then barrier
+//   reduce_stats(f) / reduce_best(f): block reductions of f(tid); the result
+//                   is only meaningful inside the following single()
+//   or_status(p,v)  atomic OR
+// The device executor is in spx_cc.cu; tools/host_emu.cu runs the same
+// sequence serially on the CPU for debugging.
+// --------------------------------------------------------------------------
+struct PairJob {
+    const float *base[5];
+    long long pitch;
+    int H, W, x1, y1, ny, nx, cc_type, status0;
+    unsigned flags;
+    bool patch_icc;        // ICC is a user-visible output: write NaN lattices
+};
+
+template <class C, class Ex>
+SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
+                         double *shift2, int *peak, int *status) {
+    PairState *ps = c.ps;
+    ex.single([&]() {
+        for (int s = 0; s < 5; ++s) {
+            ps->base[s] = job.base[s];
+            ps->pitch[s] = job.pitch;
+            ps->y0[s] = job.y1; ps->x0[s] = job.x1;
+        }
+        ps->H = job.H; ps->W = job.W;
+        ps->ny = job.ny; ps->nx = job.nx;
+        ps->yc = (job.ny - 1) / 2; ps->xc = (job.nx - 1) / 2;
+        ps->cc_type = job.cc_type; ps->flags = job.flags;
+        ps->mu = 0.f; ps->mu_ref = 0.f; ps->rscale = 1.f;
+        ps->status = job.status0;
+        ps->best = best_init();
+    });
+
+    // ---- normalisation statistics (cc.py:131-156) ----------------------
+    if (job.cc_type != SPX_CC) {
+        StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(*ps, tid); });
+        ex.single([&]() { stats_finalize(*ps, tot); });
+    }
+
+    // ---- reference image -> conj(R) * scale, half spectrum ---------------
+    ex.par([&](int tid) {
+        const int fl = c1_pass<C>(c, tid, 0, -1, 0);
+        if (fl) ex.or_status(&ps->status, fl);
+    });
+    ex.par([&](int tid) { c2_pass<C>(c, tid); });
+    for (int b0 = 0; b0 < C::RH; b0 += 32) {
+        ex.par([&](int tid) {
+            const int k = b0 + (tid & 31);
+            x1_pass<C>(c, tid, k < C::RH ? int(c.rrow[k]) : -1, 0);
+        });
+        ex.par([&](int tid) {
+            const int k = b0 + (tid & 31);
+            x2_ref_pass<C>(c, tid, k < C::RH ? ky_of_row<C>(int(c.rrow[k])) : -1);
+        });
+    }
+
+    // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
+    for (int b = 0; b < 2; ++b) {
+        ex.par([&](int tid) {
+            const int fl = c1_pass<C>(c, tid, 1 + 2 * b, 2 + 2 * b, ps->yc);
+            if (fl) ex.or_status(&ps->status, fl);
+        });
+        ex.par([&](int tid) { c2_pass<C>(c, tid); });
+        for (int b0 = 0; b0 < C::P; b0 += 32) {
+            ex.par([&](int tid) {
+                const int r = b0 + (tid & 31);
+                x1_pass<C>(c, tid, r < C::P ? r : -1, ps->xc);
+            });
+            ex.par([&](int tid) {
+                const int r = b0 + (tid & 31);
+                x2_pass<C>(c, tid, r < C::P ? r : -1);
+            });
+            ex.par([&](int tid) {
+                const int r = b0 + (tid & 31);
+                x3_pass<C>(c, tid, r < C::P ? r : -1);
+            });
+        }
+        ex.par([&](int tid) { ic1_pass<C>(c, tid); });
+        Best bb = ex.reduce_best([&](int tid) { return ic2_pass<C>(c, tid, b); });
+        ex.single([&]() { if (best_better(bb, ps->best)) ps->best = bb; });
+    }
+
+    // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
+    ex.single([&]() {
+        const float *icc = c.icc;
+        int pk, st;
+        double sh[2];
+        peak_stage(*ps, ps->best, [&](int i) { return ex.load_icc(icc + i); }, sh, &pk, &st);
+        shift2[0] = sh[0]; shift2[1] = sh[1];
+        *peak = pk; *status = st;
+        ps->status = st;
+    });
+    if (job.patch_icc) {
+        ex.par([&](int tid) {
+            const int st = ps->status;
+            const int nanbits = SPX_S_NONFINITE_REF | SPX_S_BAD_NORM | SPX_S_NONFINITE_P00 |
+                                SPX_S_NONFINITE_P10 | SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
+            if (st & nanbits) {
+                const int ne = 4 * ps->ny * ps->nx;
+                union { unsigned u; float f; } qnan; qnan.u = 0x7fc00000u;
+                for (int i = tid; i < ne; i += C::T)
+                    if (icc_is_nan(*ps, st, i)) c.icc[i] = qnan.f;
+            }
+        });
+    }
+}
+
+// rows of W (scrambled ky order) whose frequency lies in the stored half
+template <class C>
+SPX_HD void build_rrow(uint16_t *rrow) {
+    int k = 0;
+    for (int r = 0; r < C::P; ++r)
+        if (ky_of_row<C>(r) <= C::P / 2) rrow[k++] = uint16_t(r);
+}
+
+}  // namespace spx

@@ -1,0 +1,102 @@
+// Shared helpers for the subpixal_b200 kernels (sm_100a).
+//
+// Everything that does per-thread work between two block barriers is written
+// as an SPX_HD function of (context, tid) so that the SAME source can be
+// executed sequentially on the host (tools/host_emu.cu, built with
+// -DSPX_HOST_EMU) to debug index arithmetic without a GPU.  The product never
+// runs that emulation: it exists only as a developer tool.
+#pragma once
+#ifdef SPX_HOST_EMU          // plain g++ build of tools/host_emu.cu
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#else
+#include <cuda_runtime.h>
+#endif
+#include <math.h>
+#include <stdint.h>
+#include <type_traits>
+
+#define SPX_HD __host__ __device__ __forceinline__
+
+namespace spx {
+
+// ---- compile-time loop --------------------------------------------------
+template <int B, int E, class F>
+SPX_HD void static_for(F &&f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+// ---- constexpr trigonometry (exact rational angles 2*pi*k/n) -------------
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+__host__ __device__ constexpr double poly_sin(double x) {   // |x| <= pi/4
+    double x2 = x * x, term = x, sum = x;
+    for (int i = 1; i < 12; ++i) {
+        term *= -x2 / double((2 * i) * (2 * i + 1));
+        sum += term;
+    }
+    return sum;
+}
+__host__ __device__ constexpr double poly_cos(double x) {   // |x| <= pi/4
+    double x2 = x * x, term = 1.0, sum = 1.0;
+    for (int i = 1; i < 12; ++i) {
+        term *= -x2 / double((2 * i - 1) * (2 * i));
+        sum += term;
+    }
+    return sum;
+}
+// cos(2*pi*k/n), sin(2*pi*k/n) with octant reduction on the integers, so the
+// special angles are exact (0, +-1, +-sqrt(1/2) to double rounding).
+__host__ __device__ constexpr double cos2pi(long long k, long long n) {
+    k %= n; if (k < 0) k += n;
+    if (2 * k > n) k = n - k;                       // cos is even about pi
+    // now 0 <= k/n <= 1/2
+    if (4 * k > n) return -cos2pi(n - 2 * k, 2 * n); // cos(x) = -cos(pi-x)
+    // 0 <= k/n <= 1/4
+    if (8 * k > n) {                                 // cos(x) = sin(pi/2 - x)
+        long long kk = n - 4 * k;                    // angle = 2*pi*kk/(4n)
+        return poly_sin(2.0 * kPi * double(kk) / double(4 * n));
+    }
+    return poly_cos(2.0 * kPi * double(k) / double(n));
+}
+__host__ __device__ constexpr double sin2pi(long long k, long long n) {
+    return cos2pi(4 * k - n, 4 * n);                 // sin(x) = cos(x - pi/2)
+}
+
+// ---- complex helpers ------------------------------------------------------
+struct cf { float x, y; };     // plain complex float (same layout as float2)
+
+SPX_HD cf cmake(float a, float b) { cf r; r.x = a; r.y = b; return r; }
+SPX_HD cf cadd(cf a, cf b) { return cmake(a.x + b.x, a.y + b.y); }
+SPX_HD cf csub(cf a, cf b) { return cmake(a.x - b.x, a.y - b.y); }
+SPX_HD cf cmul(cf a, cf b) {
+    return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+SPX_HD cf cmulc(cf a, cf b) {  // a * conj(b)
+    return cmake(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+SPX_HD cf cconj(cf a) { return cmake(a.x, -a.y); }
+
+// ---- twiddle tables W_P^k = exp(-2*pi*i*k/P), k in [0, P) ---------------
+template <int P>
+struct TwTable {
+    float re[P], im[P];
+    constexpr TwTable() : re(), im() {
+        for (int k = 0; k < P; ++k) {
+            re[k] = float(cos2pi(k, P));
+            im[k] = float(-sin2pi(k, P));
+        }
+    }
+};
+
+SPX_HD bool finitef(float v) {
+    // works under any fast-math setting: exponent bits all ones <=> inf/nan
+    union { float f; uint32_t u; } c; c.f = v;
+    return (c.u & 0x7f800000u) != 0x7f800000u;
+}
+
+}  // namespace spx

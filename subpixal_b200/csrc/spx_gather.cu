@@ -1,0 +1,153 @@
+// (1) Batched cutout gather: the crop / fill / mask arithmetic of
+// cutout.Cutout.__init__ (reference cutout.py:737-779) plus the mask updates
+// of the list builders (cutout.py:188-196, 286-292, 416-427) and the optional
+// masked-pixel zeroing of align.py:661, for n boxes in one launch.
+//
+// HBM-bound byte work: one warp per cutout row, lanes along x, so every
+// global load/store instruction touches one contiguous row segment.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/subpixal_b200.h"
+#include "spx_common.cuh"
+
+namespace spx {
+
+constexpr int kGatherThreads = 256;
+constexpr int kGatherRows = 32;        // rows of one cutout handled by a CTA
+
+struct GatherDev {
+    const void *frame; const void *dq; const void *weight; const void *seg;
+    const long long *src_ids; const int *boxes; const long long *out_offset;
+    void *data_out; unsigned char *mask_out; void *dq_out; void *weight_out;
+    long long frame_pitch, dq_good_bits;
+    double fillval;
+    int H, W, n, dq_bytes, weight_f64, seg_bytes, dq_use_bits, zero_masked;
+};
+
+__device__ __forceinline__ long long load_int(const void *p, long long i, int bytes) {
+    switch (bytes) {
+        case 1: return static_cast<const int8_t *>(p)[i];
+        case 2: return static_cast<const int16_t *>(p)[i];
+        case 4: return static_cast<const int32_t *>(p)[i];
+        default: return static_cast<const long long *>(p)[i];
+    }
+}
+// DQ words are bit fields: zero-extend so that the bits above the element
+// width never take part in the (dq & ~good) test
+__device__ __forceinline__ long long load_bits(const void *p, long long i, int bytes) {
+    switch (bytes) {
+        case 1: return static_cast<const uint8_t *>(p)[i];
+        case 2: return static_cast<const uint16_t *>(p)[i];
+        case 4: return static_cast<const uint32_t *>(p)[i];
+        default: return static_cast<const long long *>(p)[i];
+    }
+}
+__device__ __forceinline__ void store_int(void *p, long long i, int bytes, long long v) {
+    switch (bytes) {
+        case 1: static_cast<int8_t *>(p)[i] = int8_t(v); break;
+        case 2: static_cast<int16_t *>(p)[i] = int16_t(v); break;
+        case 4: static_cast<int32_t *>(p)[i] = int32_t(v); break;
+        default: static_cast<long long *>(p)[i] = v; break;
+    }
+}
+template <class T> __device__ __forceinline__ bool is_finite(T v);
+template <> __device__ __forceinline__ bool is_finite<float>(float v) { return finitef(v); }
+template <> __device__ __forceinline__ bool is_finite<double>(double v) {
+    return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
+}
+
+template <class T>
+__global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev a) {
+    const int k = blockIdx.y;
+    const int4 box = __ldg(reinterpret_cast<const int4 *>(a.boxes) + k);
+    const int x1 = box.x, y1 = box.y, w = box.z - box.x + 1, h = box.w - box.y + 1;
+    const int row0 = blockIdx.x * kGatherRows;
+    if (row0 >= h || w <= 0) return;
+    const long long off = a.out_offset[k];
+    const long long sid = a.src_ids ? a.src_ids[k] : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row_end = min(h, row0 + kGatherRows);
+    const T *frame = static_cast<const T *>(a.frame);
+    T *out = static_cast<T *>(a.data_out);
+    const T fill = T(a.fillval);
+    for (int row = row0 + warp; row < row_end; row += kGatherThreads / 32) {
+        const int yy = y1 + row;
+        const bool inrow = yy >= 0 && yy < a.H;
+        for (int col = lane; col < w; col += 32) {
+            const int xx = x1 + col;
+            const bool inside = inrow && xx >= 0 && xx < a.W;     // cutout.py:742-752
+            const long long o = off + (long long)row * w + col;
+            T v = inside ? __ldg(frame + (long long)yy * a.frame_pitch + xx) : fill;
+            bool bad = !inside || !is_finite<T>(v);                // cutout.py:755
+            const long long src = (long long)yy * a.W + xx;
+            if (a.dq) {                                            // cutout.py:758-766
+                const long long d = inside ? load_bits(a.dq, src, a.dq_bytes) : 0;
+                if (a.dq_out) store_int(a.dq_out, o, a.dq_bytes, d);
+                if (a.dq_use_bits) bad |= (d & ~a.dq_good_bits) != 0;   // cutout.py:190-193
+            }
+            if (a.seg && a.src_ids) {                              // cutout.py:188, 416-419
+                const long long s = inside ? load_int(a.seg, src, a.seg_bytes) : 0;
+                bad |= (s != sid);
+            }
+            if (a.weight && a.weight_out) {                        // cutout.py:769-779
+                if (a.weight_f64)
+                    static_cast<double *>(a.weight_out)[o] =
+                        inside ? static_cast<const double *>(a.weight)[src] : 0.0;
+                else
+                    static_cast<float *>(a.weight_out)[o] =
+                        inside ? static_cast<const float *>(a.weight)[src] : 0.f;
+            }
+            if (a.zero_masked && bad) v = T(0);                    // align.py:661
+            out[o] = v;
+            if (a.mask_out) a.mask_out[o] = bad ? 1 : 0;
+        }
+    }
+}
+
+static int int_bytes(int kind) {
+    switch (kind) {
+        case SPX_T_I8: return 1; case SPX_T_I16: return 2;
+        case SPX_T_I32: return 4; case SPX_T_I64: return 8; default: return 0;
+    }
+}
+
+}  // namespace spx
+
+extern "C" int spx_gather_cutouts(const spx_gather_args *g, void *stream) {
+    using namespace spx;
+    if (!g || !g->frame || !g->boxes || !g->out_offset || !g->data_out) return SPX_E_BADARG;
+    if (g->n < 0 || g->frame_h < 1 || g->frame_w < 1 || g->frame_pitch < g->frame_w ||
+        g->max_h < 1 || g->max_w < 1) return SPX_E_BADARG;
+    if (g->frame_kind != SPX_T_F32 && g->frame_kind != SPX_T_F64) return SPX_E_DTYPE;
+    GatherDev a{};
+    a.frame = g->frame; a.dq = g->dq; a.weight = g->weight; a.seg = g->seg;
+    a.src_ids = reinterpret_cast<const long long *>(g->src_ids);
+    a.boxes = g->boxes; a.out_offset = reinterpret_cast<const long long *>(g->out_offset);
+    a.data_out = g->data_out; a.mask_out = g->mask_out; a.dq_out = g->dq_out;
+    a.weight_out = g->weight_out;
+    a.frame_pitch = g->frame_pitch; a.dq_good_bits = g->dq_good_bits;
+    a.fillval = g->fillval; a.H = g->frame_h; a.W = g->frame_w; a.n = g->n;
+    a.dq_use_bits = g->dq_use_bits; a.zero_masked = g->zero_masked;
+    if (g->dq) { a.dq_bytes = int_bytes(g->dq_kind); if (!a.dq_bytes) return SPX_E_DTYPE; }
+    if (g->seg) { a.seg_bytes = int_bytes(g->seg_kind); if (a.seg_bytes < 4) return SPX_E_DTYPE; }
+    if (g->weight) {
+        if (g->weight_kind != SPX_T_F32 && g->weight_kind != SPX_T_F64) return SPX_E_DTYPE;
+        a.weight_f64 = g->weight_kind == SPX_T_F64;
+    }
+    if (g->n == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rows = (g->max_h + kGatherRows - 1) / kGatherRows;
+    for (int k0 = 0; k0 < g->n; k0 += 65535) {              // gridDim.y limit
+        const int nk = (g->n - k0 < 65535) ? g->n - k0 : 65535;
+        GatherDev b = a;
+        b.boxes = a.boxes + 4 * size_t(k0);
+        b.out_offset = a.out_offset + k0;
+        if (a.src_ids) b.src_ids = a.src_ids + k0;
+        dim3 grid(rows, nk);
+        if (g->frame_kind == SPX_T_F32) gather_kernel<float><<<grid, kGatherThreads, 0, st>>>(b);
+        else gather_kernel<double><<<grid, kGatherThreads, 0, st>>>(b);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return int(e);
+    }
+    return 0;
+}

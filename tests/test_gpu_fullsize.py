@@ -1,0 +1,90 @@
+"""Full-size (BASELINE.json config) runs on the GPU, checked through
+size-independent properties plus an oracle comparison on a subsample."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import subpixal_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample_check(frames, boxes, sh, pk, t, idx):
+    from subpixal_b200 import synthetic as syn
+    host = frames.cpu().numpy()
+    stack = syn.cut_stack(host, boxes[idx])
+    worst, mism = 0.0, 0
+    for j, k in enumerate(idx):
+        with warnings.catch_warnings(), np.errstate(all="ignore"):
+            warnings.simplefilter("ignore")
+            dx, dy, icc, _ = orc.find_displacement(*stack[j], cc_type=t, full_output=True)
+        if int(np.argmax(icc)) != int(pk[k]):
+            srt = np.sort(icc.ravel())
+            assert (srt[-1] - srt[-2]) <= 1e-5 * abs(srt[-1])
+            mism += 1
+            continue
+        worst = max(worst, abs(sh[k, 0] - dx), abs(sh[k, 1] - dy))
+    return worst, mism
+
+
+def test_config2_10k_pairs_64():
+    """10k cutout pairs 64x64 from one synthetic 4096x2048 frame (config 2)."""
+    from subpixal_b200 import batch, synthetic as syn
+    sc = syn.make_scene(10000, 2048, 4096, 64, seed=20242)
+    frames, truth = syn.make_frames(sc, "cuda")
+    boxes = syn.make_boxes(sc)
+    tb = torch.from_numpy(boxes).cuda()
+    sh, pk, st, _ = batch.cc_fit_frames(frames, tb, 64, 64, "NCC")
+    sh_h, pk_h, st_h = sh.cpu().numpy(), pk.cpu().numpy(), st.cpu().numpy()
+    assert np.all(np.isfinite(sh_h)) and np.all((st_h & 0x63f) == 0)
+    # determinism / idempotence: a second launch gives bit-identical results
+    sh2, pk2, _, _ = batch.cc_fit_frames(frames, tb, 64, 64, "NCC")
+    assert torch.equal(sh, sh2) and torch.equal(pk, pk2)
+    # permutation invariance: pairs are independent
+    perm = torch.randperm(10000, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    sh3, _, _, _ = batch.cc_fit_frames(frames, tb[perm], 64, 64, "NCC")
+    assert torch.equal(sh3, sh[perm])
+    # scale invariance of NCC: multiplying every frame by 4 (exact in fp32)
+    sh4, pk4, _, _ = batch.cc_fit_frames(frames * 4.0, tb, 64, 64, "NCC")
+    assert torch.equal(pk4, pk) and float((sh4 - sh).abs().max()) < 1e-5
+    # translation covariance: the same pixels through shifted frames + boxes
+    pad = torch.zeros((5, 2048 + 7, 4096 + 5), device="cuda")
+    pad[:, 7:, 5:] = frames
+    tb5 = tb.clone(); tb5[:, [0, 2]] += 5; tb5[:, [1, 3]] += 7
+    sh5, _, _, _ = batch.cc_fit_frames(pad, tb5, 64, 64, "NCC")
+    assert torch.equal(sh5, sh)
+    # the recovered shifts follow the injected frame misalignment
+    err = sh_h - truth
+    assert abs(np.median(err[:, 0])) < 0.02 and abs(np.median(err[:, 1])) < 0.02
+    # oracle parity on a subsample
+    idx = np.arange(0, 10000, 37)
+    worst, mism = _sample_check(frames, boxes, sh_h, pk_h, "NCC", idx)
+    assert worst < 1e-3 and worst < 1e-4 and mism <= 3
+
+
+def test_config3_128_masked():
+    """128x128 cutouts with per-cutout masking (config 3, reduced count)."""
+    from subpixal_b200 import batch, synthetic as syn
+    sc = syn.make_scene(3000, 2048, 4096, 128, seed=20243)
+    frames, truth = syn.make_frames(sc, "cuda")
+    # 0.1 % NaN pixels in the reference-phase frames (masked + zeroed by the gather)
+    gen = torch.Generator("cuda").manual_seed(3)
+    for k in range(1, 5):
+        frames[k][torch.rand(frames[k].shape, device="cuda", generator=gen) < 1e-3] = float("nan")
+    boxes = syn.make_boxes(sc)
+    tb = torch.from_numpy(boxes).cuda()
+    for t in ("NCC", "ZNCC"):
+        sh, pk, st, _ = batch.cc_fit_frames(frames, tb, 128, 128, t, zero_bad_phases=True)
+        sh_h, pk_h = sh.cpu().numpy(), pk.cpu().numpy()
+        assert np.all(np.isfinite(sh_h)) and np.all((st.cpu().numpy() & 0x3f) == 0)
+        clean = torch.nan_to_num(frames, nan=0.0)
+        idx = np.arange(0, 3000, 60)
+        worst, mism = _sample_check(clean, boxes, sh_h, pk_h, t, idx)
+        assert worst < 1e-3 and mism <= 1
+    # without the zeroing flag the NaNs poison the pair exactly like the reference
+    sh, pk, st, _ = batch.cc_fit_frames(frames, tb[:64], 128, 128, "NCC", zero_bad_phases=False)
+    bad = (st.cpu().numpy() & 0x3e) != 0
+    assert bad.any()
+    assert np.all(sh.cpu().numpy()[bad] == np.array([-63.0, -63.0]))

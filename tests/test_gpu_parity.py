@@ -1,0 +1,286 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the reference-
+signature wrappers and the batched API) against the committed golden fixtures
+produced by the unmodified reference, and against the CPU oracle on seeded
+inputs.  Tolerances are BASELINE.json's: shift within 1e-3 px, ICC relative
+L2 <= 1e-5, identical integer peak index (we assert tighter bounds where the
+implementation allows)."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import subpixal_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SHIFT_TOL = 1e-3        # BASELINE.json north_star
+ICC_L2_TOL = 1e-5
+CC_TYPES = ("CC", "NCC", "ZNCC")
+
+
+def _oracle(stack, t):
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        return orc.find_displacement(*stack, cc_type=t, full_output=True)
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def test_native_library_is_loaded():
+    import subpixal_b200._lib as L
+    assert L.load().spx_abi_version() == L.ABI_VERSION
+    assert torch.cuda.is_available()
+
+
+def test_known_shift_table():
+    from subpixal_b200 import cc
+    g = golden("known_shift")
+    for n, t, dx, dy, am in g["table"]:
+        ref, ims = orc.known_shift_case(int(n))
+        gdx, gdy, icc, ccs = cc.find_displacement(ref, *ims, cc_type=CC_TYPES[int(t)],
+                                                  full_output=True)
+        assert abs(gdx - dx) < SHIFT_TOL and abs(gdy - dy) < SHIFT_TOL
+        assert abs(gdx - dx) < 2e-5 and abs(gdy - dy) < 2e-5
+        assert icc.shape == (2 * int(n), 2 * int(n)) and icc.dtype == np.float32
+        assert len(ccs) == 4 and ccs[0].shape == (int(n), int(n))
+    # config 1 of BASELINE.json: (0.37, -0.21) px injected, N=64
+    ref, ims = orc.known_shift_case(64)
+    dx, dy = cc.find_displacement(ref, *ims)
+    assert isinstance(dx, float) and abs(dx - 0.37143377832708424) < 2e-5
+    assert abs(dy + 0.20770010609720302) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["rand32", "rand64", "rand33", "rect20x37",
+                                  "mask48", "rand128"])
+def test_golden_random_sets(name):
+    from subpixal_b200 import batch
+    g = golden(name)
+    stacks = torch.from_numpy(g["stacks"]).cuda()
+    for t in CC_TYPES:
+        sh, pk, st, icc = batch.cc_fit_stack(stacks, t, want_icc=True)
+        sh, pk, icc = sh.cpu().numpy(), pk.cpu().numpy(), icc.cpu().numpy()
+        want = g["dxdy_" + t]
+        assert np.max(np.abs(sh - want)) < SHIFT_TOL
+        assert np.max(np.abs(sh - want)) < 5e-5
+        assert np.array_equal(pk.astype(np.int64), g["argmax_" + t])
+        if "icc_" + t in g.files:
+            for k in range(len(want)):
+                assert _rel_l2(icc[k], g["icc_" + t][k]) < ICC_L2_TOL
+        # the throughput path (no ICC written) gives the same answer
+        sh2, pk2, _, none = batch.cc_fit_stack(stacks, t)
+        assert none is None
+        assert np.array_equal(sh2.cpu().numpy(), sh) and np.array_equal(pk2.cpu().numpy(), pk)
+
+
+def test_ccs_are_unreversed_phase_images():
+    from subpixal_b200 import cc
+    st, _ = orc.random_pairs(1, 24, 30, seed=3)
+    dx, dy, icc, ccs = cc.find_displacement(*st[0], cc_type="CC", full_output=True)
+    odx, ody, oicc, occs = _oracle(st[0], "CC")
+    for a, b in zip(ccs, occs):
+        assert a.shape == b.shape and _rel_l2(a, b) < ICC_L2_TOL
+    assert abs(dx - odx) < 5e-5 and abs(dy - ody) < 5e-5
+
+
+def test_degenerate_inputs_match_reference():
+    from subpixal_b200 import cc
+    g = golden("degenerate")
+    order = ["nan_slot0", "nan_slot1", "nan_slot2", "nan_slot3", "nan_slot4",
+             "zero_phases", "inf_slot3", "bogus_type"]
+    for name, (dx, dy, am, nanfrac) in zip(g["names"], g["results"]):
+        case, t = str(name).split(":")
+        st = g["stacks"][order.index(case)] if case != "lower_case" else g["stacks"][-1]
+        gdx, gdy, icc, _ = cc.find_displacement(*st, cc_type=t, full_output=True)
+        assert abs(gdx - dx) < 5e-5 and abs(gdy - dy) < 5e-5, name
+        assert float(np.mean(np.isnan(icc))) == nanfrac, name
+        with np.errstate(all="ignore"):
+            assert int(np.argmax(icc.astype(np.float64))) == int(am), name
+    st = g["stacks"][0]
+    with pytest.raises(ValueError, match="same shape"):
+        cc.find_displacement(st[0], st[1][:-1], st[2], st[3], st[4])
+    before = st.copy()
+    cc.find_displacement(*st, cc_type="ZNCC")
+    assert np.array_equal(before, st, equal_nan=True)      # inputs never modified
+
+
+def test_float64_inputs_keep_dtype():
+    from subpixal_b200 import cc
+    st, _ = orc.random_pairs(1, 32, 32, seed=11)
+    st64 = st[0].astype(np.float64)
+    dx, dy, icc, _ = cc.find_displacement(*st64, full_output=True)
+    odx, ody, oicc, _ = _oracle(st64, "NCC")
+    assert icc.dtype == np.float64
+    assert abs(dx - odx) < SHIFT_TOL and abs(dy - ody) < SHIFT_TOL
+    assert _rel_l2(icc, oicc) < ICC_L2_TOL
+
+
+@pytest.mark.parametrize("ny,nx,n", [(64, 64, 300), (32, 32, 300), (16, 16, 64),
+                                     (3, 3, 8), (7, 50, 32), (96, 80, 24),
+                                     (128, 128, 24), (200, 256, 4)])
+def test_batched_stack_against_oracle(ny, nx, n):
+    from subpixal_b200 import batch
+    stacks, _ = orc.random_pairs(n, ny, nx, seed=1000 * ny + nx)
+    dev = torch.from_numpy(stacks).cuda()
+    for t in ("NCC", "ZNCC", "CC"):
+        sh, pk, st, icc = batch.cc_fit_stack(dev, t, want_icc=(n <= 64))
+        sh, pk = sh.cpu().numpy(), pk.cpu().numpy()
+        mism, worst, worst_l2 = 0, 0.0, 0.0
+        for k in range(n):
+            dx, dy, oicc, _ = _oracle(stacks[k], t)
+            if int(np.argmax(oicc)) != int(pk[k]):
+                # only legitimate for a numerical near-tie of the two top samples
+                srt = np.sort(oicc.ravel())
+                assert (srt[-1] - srt[-2]) <= 1e-5 * abs(srt[-1])
+                mism += 1
+                continue
+            worst = max(worst, abs(sh[k, 0] - dx), abs(sh[k, 1] - dy))
+            if icc is not None:
+                worst_l2 = max(worst_l2, _rel_l2(icc[k].cpu().numpy(), oicc))
+        assert worst < SHIFT_TOL and worst < 1e-4
+        assert worst_l2 < ICC_L2_TOL
+        assert mism <= max(1, n // 100)
+
+
+def test_fused_frames_equals_gather_then_stack():
+    from subpixal_b200 import batch, synthetic as syn
+    sc = syn.make_scene(400, 700, 900, 64, seed=20242)
+    frames, truth = syn.make_frames(sc, "cuda")
+    boxes = syn.make_boxes(sc)
+    # push some boxes over the frame edge ('fill' mode) and add bad pixels
+    boxes[:5, [0, 2]] -= boxes[:5, [0]] + 10
+    boxes[5:9, [1, 3]] += 700 - boxes[5:9, [3]] + 7
+    frames[1, 100:110, 200:220] = float("nan")
+    tb = torch.from_numpy(boxes).cuda()
+    for t in ("NCC", "CC", "ZNCC"):
+        sh, pk, st, icc = batch.cc_fit_frames(frames, tb, 64, 64, t, want_icc=True)
+        cuts = [batch.gather_cutouts(frames[k], boxes, fillval=0.0, zero_masked=(k > 0))
+                for k in range(5)]
+        stack = torch.stack([c["data"].reshape(-1, 64, 64) for c in cuts], dim=1)
+        sh2, pk2, st2, icc2 = batch.cc_fit_stack(stack, t, want_icc=True)
+        assert torch.equal(sh, sh2) and torch.equal(pk, pk2)
+        assert torch.equal(icc, icc2)
+        host = stack.cpu().numpy()
+        for k in list(range(12)) + list(range(100, 130)):
+            dx, dy, oicc, _ = _oracle(host[k], t)
+            assert abs(sh[k, 0].item() - dx) < 1e-4 and abs(sh[k, 1].item() - dy) < 1e-4
+    # box of the wrong size is reported, not silently processed
+    bad = tb.clone()
+    bad[3, 2] += 1
+    _, _, st, _ = batch.cc_fit_frames(frames, bad, 64, 64)
+    assert int(st[3]) & 0x400 and not int(st[2]) & 0x400
+
+
+def test_find_peak_fixtures():
+    from subpixal_b200 import centroid
+    g = golden("find_peak")
+    for im, pk in zip(g["images"], g["peaks"]):
+        got = centroid.find_peak(im, peak_fit_box=5, peak_search_box="all")
+        assert np.allclose(got, pk, rtol=0, atol=1e-9), (got, pk)
+    im, msk = g["var_image"], g["var_mask"]
+    for kw, pk in zip(g["var_kwargs"], g["var_peaks"]):
+        kwargs = eval(str(kw), {"MASK": None})
+        if "mask" in kwargs:
+            kwargs["mask"] = msk
+        got = centroid.find_peak(im, **kwargs)
+        assert np.allclose(got, pk, rtol=0, atol=1e-9), (kw, got, pk)
+    got = centroid.find_peak(im.astype(np.float32))
+    assert np.allclose(got, orc.find_peak(im.astype(np.float32)), atol=1e-9)
+
+
+def test_find_peak_batch_random():
+    from subpixal_b200 import batch
+    rng = np.random.default_rng(77)
+    imgs = rng.standard_normal((64, 23, 31))
+    for k in range(64):
+        y, x = rng.uniform(0, 22), rng.uniform(0, 30)
+        yy, xx = np.mgrid[:23, :31]
+        imgs[k] = 5 * np.exp(-((xx - x) ** 2 + (yy - y) ** 2) / 8.0) + 0.05 * imgs[k]
+    for fit in ((5, 5), (3, 7)):
+        xy, pk, st = batch.find_peak_batch(torch.from_numpy(imgs).cuda(), fit_box=fit)
+        xy = xy.cpu().numpy()
+        for k in range(64):
+            want = orc.find_peak(imgs[k], peak_fit_box=fit)
+            assert np.allclose(xy[k], want, atol=1e-9), (k, fit, xy[k], want)
+
+
+def test_cutout_fixtures():
+    from subpixal_b200 import cutout
+    g = golden("cutout")
+    frame, dq, wht = g["frame"], g["dq"], g["wht"]
+    for k, (x1, y1, x2, y2) in enumerate(g["boxes"]):
+        c = cutout.Cutout(frame, None, blc=(int(x1), int(y1)), trc=(int(x2), int(y2)),
+                          dq=dq, weight=wht, mode="fill", fillval=0)
+        assert c.data.dtype == frame.dtype and c.dq.dtype == dq.dtype
+        assert np.array_equal(c.data, g["data%d" % k], equal_nan=True)
+        assert np.array_equal(c.mask, g["mask%d" % k]) and c.mask.dtype == np.bool_
+        assert np.array_equal(c.dq, g["dq%d" % k])
+        assert np.array_equal(c.weight, g["wht%d" % k])
+        es, is_ = c.extraction_slice, c.insertion_slice
+        assert [es[0].start, es[0].stop, es[1].start, es[1].stop, is_[0].start,
+                is_[0].stop, is_[1].start, is_[1].stop] == list(g["slices%d" % k])
+        assert (c.width, c.height) == (x2 - x1 + 1, y2 - y1 + 1)
+    c = cutout.Cutout(frame.astype(np.float64), None, blc=(-2, -2), trc=(3, 3),
+                      mode="fill")                      # default fillval = nan
+    assert np.isnan(c.data[0, 0]) and c.mask[0, 0] and not c.mask[2, 2]
+    with pytest.raises(cutout.PartialOverlapError):
+        cutout.Cutout(frame, None, blc=(-1, 0), trc=(5, 5))
+    with pytest.raises(cutout.NoOverlapError):
+        cutout.Cutout(frame, None, blc=(50, 0), trc=(55, 5), mode="fill")
+
+
+def test_gather_masks_and_ragged_boxes():
+    from subpixal_b200 import batch
+    rng = np.random.default_rng(5)
+    H, W = 60, 80
+    frame = rng.standard_normal((H, W)).astype(np.float32)
+    frame[10, 10] = np.nan
+    dq = rng.integers(0, 32, (H, W)).astype(np.int16)
+    seg = rng.integers(0, 4, (H, W)).astype(np.int32)
+    boxes = np.array([[0, 0, 9, 4], [5, 5, 20, 30], [-3, -4, 6, 3], [70, 50, 85, 66],
+                      [8, 8, 12, 12]], dtype=np.int64)
+    ids = np.array([1, 2, 3, 0, 2])
+    res = batch.gather_cutouts(torch.from_numpy(frame).cuda(), boxes,
+                               dq=torch.from_numpy(dq).cuda(),
+                               seg=torch.from_numpy(seg).cuda(), src_ids=ids,
+                               dq_good_bits=6, fillval=0.0, zero_masked=True)
+    off = res["offsets"].numpy()
+    data, mask = res["data"].cpu().numpy(), res["mask"].cpu().numpy().astype(bool)
+    for k, (x1, y1, x2, y2) in enumerate(boxes):
+        o = orc.crop(frame, (x1, y1), (x2, y2), dq=dq, mode="fill", fillval=0)
+        sg = np.zeros_like(o["data"], dtype=seg.dtype)
+        sg[o["insertion_slice"]] = seg[o["extraction_slice"]]
+        bad = o["mask"] | orc.bitfield_bad_mask(o["dq"], 6) | (sg != ids[k])
+        want = o["data"].copy()
+        want[bad] = 0
+        h, w = y2 - y1 + 1, x2 - x1 + 1
+        assert np.array_equal(mask[off[k]:off[k + 1]].reshape(h, w), bad)
+        assert np.array_equal(data[off[k]:off[k + 1]].reshape(h, w), want)
+
+
+def test_cabi_error_codes():
+    import ctypes as C
+    import subpixal_b200._lib as L
+    lib = L.load()
+    z = C.c_void_p(0)
+    strides = (C.c_int64 * 5)(0, 0, 0, 0, 0)
+    buf = torch.zeros(1024, device="cuda")
+    p = C.c_void_p(buf.data_ptr())
+    assert lib.spx_cc_fit_stack(z, p, p, p, p, C.byref(strides), 1, 8, 8, 0,
+                                p, p, p, z, z, 0, z) == L.E_BADARG
+    assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 1, 300, 8, 0,
+                                p, p, p, z, z, 0, z) == L.E_UNSUPPORTED
+    assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 1, 2, 8, 0,
+                                p, p, p, z, z, 0, z) == L.E_UNSUPPORTED
+    assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 1, 8, 8, 0,
+                                p, p, p, z, z, 0, z) == L.E_WORKSPACE
+    assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 0, 8, 8, 0,
+                                p, p, p, z, z, 0, z) == 0
+    assert lib.spx_find_peak(p, 7, 1, 8, 8, z, z, 0, 0, 5, 5, p, p, p, z) == L.E_DTYPE
+    assert lib.spx_find_peak(p, 0, 1, 8, 8, z, z, 0, 0, 99, 5, p, p, p, z) == L.E_UNSUPPORTED
+    with pytest.raises(L.SubpixalError):
+        L.check(L.E_WORKSPACE)

@@ -1,0 +1,163 @@
+"""CPU-only tests: host-side logic of the package, the C-ABI library's symbol
+table, and that compute entry points fail loudly without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import subpixal_oracle as orc
+
+HEADER = os.path.join(ROOT, "include", "subpixal_b200.h")
+
+
+def test_library_exports_every_declared_symbol():
+    import subpixal_b200._lib as L
+    lib = L.load()
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    declared = set(re.findall(r"\b(spx_[a-z_0-9]+)\s*\(", text))
+    assert declared == set(L.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.spx_abi_version() == L.ABI_VERSION == int(
+        re.search(r"#define SPX_ABI_VERSION (\d+)", text).group(1))
+    for const in ("E_BADARG", "E_UNSUPPORTED", "E_WORKSPACE", "E_DTYPE", "S_PEAK_EDGE",
+                  "S_NO_MAXIMUM", "S_FIT_OUTSIDE", "S_BOX_MISMATCH", "MAX_CUTOUT"):
+        m = re.search(r"#define SPX_%s\s+\(?(-?(?:0x)?[0-9a-fA-F]+)\)?" % const, text)
+        assert int(m.group(1), 0) == getattr(L, const), const
+    assert b"workspace" in lib.spx_error_string(L.E_WORKSPACE)
+    assert lib.spx_error_string(0) == b"ok"
+
+
+def test_workspace_query_and_argument_checks_without_gpu():
+    import subpixal_b200._lib as L
+    lib = L.load()
+    assert lib.spx_cc_workspace_bytes(0, 64, 64, 0) == 0
+    assert lib.spx_cc_workspace_bytes(10, 300, 64, 0) == 0
+    small, big = (lib.spx_cc_workspace_bytes(n, 64, 64, 0) for n in (1, 100000))
+    assert 0 < small < big
+    assert lib.spx_cc_workspace_bytes(100000, 64, 64, 1) == 0   # ICC goes to the user buffer
+    assert lib.spx_cc_workspace_bytes(4, 128, 128, 1) > 0       # W slab for big cutouts
+    z = C.c_void_p(0)
+    assert lib.spx_cc_fit_stack(z, z, z, z, z, None, 1, 8, 8, 0, z, z, z, z, z, 0, z) == L.E_BADARG
+    assert lib.spx_gather_cutouts(None, z) == L.E_BADARG
+    assert lib.spx_find_peak(z, 0, 1, 4, 4, z, z, 0, 0, 5, 5, z, z, z, z) == L.E_BADARG
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_compute_fails_loudly_without_cuda():
+    from subpixal_b200 import cc, centroid, cutout
+    ref, ims = orc.known_shift_case(16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cc.find_displacement(ref, *ims)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        centroid.find_peak(ref)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cutout.Cutout(ref, None, blc=(0, 0), trc=(3, 3))
+
+
+def test_argument_errors_match_reference():
+    from subpixal_b200 import cc, centroid, cutout
+    ref, ims = orc.known_shift_case(16)
+    with pytest.raises(ValueError, match="All cutouts must have same shape"):
+        cc.find_displacement(ref, ims[0][:-1], *ims[1:])
+    with pytest.raises(ValueError, match="Both 'xmax' and 'ymax'"):
+        centroid.find_peak(ref, xmax=1.0)
+    with pytest.raises(TypeError):
+        centroid.find_peak(ref, peak_fit_box=(1, 2, 3))
+    with pytest.raises(ValueError):
+        centroid.find_peak(ref, peak_fit_box=0)
+    with pytest.raises(ValueError, match="'trc' cannot be None"):
+        cutout.Cutout(None, None)
+    with pytest.raises(ValueError, match="mode"):
+        cutout.Cutout(ref, None, mode="loose")
+    with pytest.raises(cutout.NoOverlapError):
+        cutout.Cutout(ref, None, blc=(16, 0), trc=(20, 4), mode="fill")
+    with pytest.raises(cutout.PartialOverlapError):
+        cutout.Cutout(ref, None, blc=(-1, 0), trc=(4, 4))
+    with pytest.raises(ValueError, match="Ill-formed"):
+        cutout.Cutout(ref, None, blc=(5, 5), trc=(4, 8), mode="fill")
+    assert issubclass(cutout.NoOverlapError, ValueError)
+    assert issubclass(cutout.PartialOverlapError, ValueError)
+
+
+def test_empty_cutout_and_properties():
+    from subpixal_b200 import cutout
+    c = cutout.Cutout(None, None, blc=(2, 3), trc=(9, 7), src_id=5, exptime=10.0)
+    assert c.data.shape == (5, 8) and c.data.dtype == np.float32
+    assert np.all(np.isnan(c.data)) and np.all(c.mask)
+    assert (c.width, c.height, c.naxis, c.naxis1, c.naxis2) == (8, 5, [8, 5], 8, 5)
+    assert c.src_pos == (5.5, 5.0) and c.cutout_src_pos == (3.5, 2.0)
+    c.cutout_src_pos = (1.0, 1.5)
+    assert c.src_pos == (3.0, 4.5)
+    assert np.array_equal(c.get_bbox('blc'), [[-.5, -.5], [-.5, 4.5], [7.5, 4.5], [7.5, -.5]])
+    assert np.array_equal(c.get_bbox(), [[1.5, 2.5], [1.5, 7.5], [9.5, 7.5], [9.5, 2.5]])
+    c.dx -= 0.5
+    assert c.dx == -0.5 and c.dy == 0
+    c.data = np.zeros((5, 8))
+    with pytest.raises(ValueError):
+        c.data = np.zeros((4, 8))
+    with pytest.raises(ValueError):
+        c.exptime = 0
+    with pytest.raises(ValueError):
+        c.data_units = "flux"
+    with pytest.raises(ValueError):
+        c.src_weight = -1.0
+    with pytest.raises(ValueError):
+        c.pscale
+
+    class W:
+        def all_pix2world(self, x, y, o):
+            return x * 2.0, y * 2.0
+
+        def all_world2pix(self, r, d, o, **kw):
+            return r / 2.0, d / 2.0
+    c2 = cutout.Cutout(None, W(), blc=(2, 3), trc=(9, 7))
+    w = c2.pix2world([[1.0, 1.0]])
+    assert np.allclose(w, [[6.0, 8.0]])
+    assert np.allclose(c2.world2pix(w), [[1.0, 1.0]])
+    c2.dx = -0.5
+    assert np.allclose(c2.pix2world([0.0], [0.0]), [[5.0], [6.0]])
+
+
+def test_slices_and_bit_flags_and_segments():
+    from subpixal_b200 import cutout
+    for blc, trc in [((-10, -5), (53, 58)), ((2, 1), (9, 12)), ((90, 95), (120, 99))]:
+        ex, ins = cutout._overlap_slices(100, 100, blc, trc)
+        o = orc.crop(np.zeros((100, 100), np.float32), blc, trc, mode="fill", fillval=0)
+        assert ex == o["extraction_slice"] and ins == o["insertion_slice"]
+    f = cutout.interpret_bit_flags
+    assert f(None) is None and f("None") is None and f(6) == 6
+    assert f("4,8") == 12 and f("4+8") == 12 and f("~4+8") == ~12 and f("~0") == -1
+    assert f(-13) == ~12
+    seg = np.zeros((12, 15), dtype=np.int32)
+    seg[2:5, 3:9] = 7
+    seg[8:11, 1:4] = 2
+    seg[0, 14] = 9
+    lab, x1, x2, y1, y2 = cutout._segment_boxes(seg)
+    assert list(lab) == [2, 7, 9]
+    assert (list(x1), list(x2), list(y1), list(y2)) == ([1, 3, 14], [3, 8, 14], [8, 2, 0], [10, 4, 0])
+
+
+def test_py2round_and_cc_type_codes():
+    from subpixal_b200 import batch, utils
+    assert utils.py2round(0.5) == 1.0 and utils.py2round(-0.5) == -1.0
+    assert list(utils.py2round(np.array([0.5, -1.5, 1.49]))) == [1.0, -2.0, 1.0]
+    assert batch.cc_type_code("zncc") == 2 and batch.cc_type_code("NCC") == 1
+    assert batch.cc_type_code("bogus") == 0 and batch.cc_type_code("cc") == 0
+
+
+def test_shard_range_covers_everything():
+    from subpixal_b200 import dist as d
+    for n in (0, 1, 7, 8, 9, 10000, 100003):
+        for world in (1, 2, 4, 8):
+            got, per = [], None
+            for r in range(world):
+                lo, hi, per = d.shard_range(n, r, world)
+                assert 0 <= hi - lo <= per
+                got += list(range(lo, hi))
+            assert got == list(range(n))
+            assert per * world >= n

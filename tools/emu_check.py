@@ -1,0 +1,58 @@
+"""Developer tool: compare tools/host_emu (CPU emulation of the CUDA pass
+sequence) with the oracle.  Not used by the product or by the test-suite."""
+import os, struct, subprocess, sys, warnings
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import subpixal_oracle as orc
+
+def run(stacks, cc_type):
+    n, _, ny, nx = stacks.shape
+    with open('/tmp/emu_in.bin', 'wb') as f:
+        f.write(struct.pack('5i', n, ny, nx, cc_type, 0))
+        f.write(np.ascontiguousarray(stacks, dtype=np.float32).tobytes())
+    subprocess.check_call(['/tmp/host_emu', '/tmp/emu_in.bin', '/tmp/emu_out.bin'])
+    buf = open('/tmp/emu_out.bin', 'rb').read()
+    o = 0
+    sh = np.frombuffer(buf, np.float64, 2 * n, o).reshape(n, 2); o += 16 * n
+    pk = np.frombuffer(buf, np.int32, n, o); o += 4 * n
+    st = np.frombuffer(buf, np.int32, n, o); o += 4 * n
+    icc = np.frombuffer(buf, np.float32, n * 4 * ny * nx, o).reshape(n, 2 * ny, 2 * nx)
+    return sh, pk, st, icc
+
+def check(stacks, label):
+    for t, name in enumerate(('CC', 'NCC', 'ZNCC')):
+        sh, pk, st, icc = run(stacks, t)
+        worst = [0, 0, 0]
+        for k, s in enumerate(stacks):
+            with warnings.catch_warnings(), np.errstate(all='ignore'):
+                warnings.simplefilter('ignore')
+                dx, dy, ricc, _ = orc.find_displacement(*s, cc_type=name, full_output=True)
+            am = int(np.argmax(ricc))
+            l2 = np.linalg.norm(icc[k].astype(np.float64) - ricc) / max(np.linalg.norm(ricc), 1e-300)
+            worst[0] = max(worst[0], abs(sh[k, 0] - dx), abs(sh[k, 1] - dy))
+            worst[1] = max(worst[1], l2)
+            worst[2] += int(am != pk[k])
+        print('%-10s %-5s max|dshift|=%.2e  max relL2=%.2e  argmax mismatches=%d  status=%s'
+              % (label, name, worst[0], worst[1], worst[2], sorted(set(st.tolist()))))
+
+if __name__ == '__main__' and len(sys.argv) == 1:
+    for (n, ny, nx) in [(4, 32, 32), (3, 64, 64), (3, 20, 37), (3, 33, 33), (3, 48, 48), (2, 5, 7), (1, 128, 128), (1, 100, 90)]:
+        stacks, _ = orc.random_pairs(n, ny, nx, seed=ny * 1000 + nx, masked=(ny == 48))
+        check(stacks, '%dx%d' % (ny, nx))
+
+def degenerate():
+    g = np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', 'degenerate.npz'))
+    order = ["nan_slot0", "nan_slot1", "nan_slot2", "nan_slot3", "nan_slot4", "zero_phases", "inf_slot3", "bogus_type"]
+    tmap = {'CC': 0, 'NCC': 1, 'ZNCC': 2, 'bogus': 7, 'zncc': 2}
+    for name, (dx, dy, am, nanfrac) in zip(g['names'], g['results']):
+        case, t = str(name).split(':')
+        st = g['stacks'][order.index(case)] if case != 'lower_case' else g['stacks'][-1]
+        sh, pk, status, icc = run(st[None], tmap[t])
+        ok = abs(sh[0, 0] - dx) < 1e-5 and abs(sh[0, 1] - dy) < 1e-5 and pk[0] == am and abs(np.mean(np.isnan(icc)) - nanfrac) < 1e-12
+        print('%-18s %s got (%.4f, %.4f, %d, nan=%.2f) want (%.4f, %.4f, %d, nan=%.2f) status=0x%x'
+              % (name, 'OK ' if ok else 'BAD', sh[0, 0], sh[0, 1], pk[0], np.mean(np.isnan(icc)), dx, dy, am, nanfrac, status[0]))
+
+if len(sys.argv) > 1 and sys.argv[1] == 'deg':
+    degenerate()
+    stacks, _ = orc.random_pairs(1, 256, 256, seed=5)
+    check(stacks, '256x256')

@@ -1,0 +1,79 @@
+// Developer tool (NOT part of the product): runs the exact pass sequence of the
+// CUDA cross-correlation kernel (spx::process_pair) serially on the CPU so the
+// index arithmetic can be debugged in a container without a GPU.
+//   g++ -std=c++17 -DSPX_HOST_EMU -O2 -x c++ -o /tmp/host_emu tools/host_emu.cu
+//   /tmp/host_emu in.bin out.bin
+// in.bin : int32 n, ny, nx, cc_type, want_frames(0) ; float32 [n,5,ny,nx]
+// out.bin: float64 [n,2] shifts ; int32 [n] peak ; int32 [n] status ; float32 [n,2ny,2nx]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../subpixal_b200/csrc/spx_cc_engine.cuh"
+
+using namespace spx;
+
+template <class C>
+struct HostExec {
+    template <class F> void par(F f) { for (int t = 0; t < C::T; ++t) f(t); }
+    template <class F> void single(F f) { f(); }
+    template <class F> StatPartial reduce_stats(F f) {
+        StatPartial tot = stat_zero();
+        for (int t = 0; t < C::T; ++t) { StatPartial s = f(t); stat_merge(tot, s); }
+        return tot;
+    }
+    template <class F> Best reduce_best(F f) {
+        Best g = best_init();
+        for (int t = 0; t < C::T; ++t) { Best b = f(t); if (best_better(b, g)) g = b; }
+        return g;
+    }
+    void or_status(int *p, int v) { *p |= v; }
+    float load_icc(const float *p) { return *p; }
+};
+
+template <class C>
+void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts, int *peak,
+         int *status, float *icc) {
+    std::vector<cf> W(C::W_ELEMS), S(C::S_ELEMS), R(C::R_ELEMS);
+    std::vector<uint16_t> rrow(C::RH);
+    build_rrow<C>(rrow.data());
+    PairState ps;
+    Ctx<C> c;
+    c.W = W.data(); c.S = S.data(); c.R = R.data(); c.rrow = rrow.data(); c.ps = &ps;
+    HostExec<C> ex;
+    const size_t tile = size_t(ny) * nx;
+    for (int p = 0; p < n; ++p) {
+        c.icc = icc + size_t(p) * 4 * tile;
+        PairJob job;
+        for (int s = 0; s < 5; ++s) job.base[s] = stack + (size_t(p) * 5 + s) * tile;
+        job.pitch = nx; job.H = ny; job.W = nx; job.x1 = 0; job.y1 = 0;
+        job.ny = ny; job.nx = nx; job.cc_type = cc_type; job.status0 = 0;
+        job.flags = 0; job.patch_icc = true;
+        process_pair<C>(c, ex, job, shifts + 2 * p, peak + p, status + p);
+    }
+}
+
+int main(int argc, char **argv) {
+    if (argc < 3) return 2;
+    FILE *f = fopen(argv[1], "rb");
+    int hdr[5];
+    if (!f || fread(hdr, 4, 5, f) != 5) return 3;
+    const int n = hdr[0], ny = hdr[1], nx = hdr[2], cc_type = hdr[3];
+    std::vector<float> stack(size_t(n) * 5 * ny * nx);
+    if (fread(stack.data(), 4, stack.size(), f) != stack.size()) return 4;
+    fclose(f);
+    std::vector<double> shifts(2 * n);
+    std::vector<int> peak(n), status(n);
+    std::vector<float> icc(size_t(n) * 4 * ny * nx);
+    const int m = ny > nx ? ny : nx;
+    if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, false, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else run<CcCfg<384, 24, 16, 256, 256, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    f = fopen(argv[2], "wb");
+    fwrite(shifts.data(), 8, shifts.size(), f);
+    fwrite(peak.data(), 4, n, f);
+    fwrite(status.data(), 4, n, f);
+    fwrite(icc.data(), 4, icc.size(), f);
+    fclose(f);
+    return 0;
+}

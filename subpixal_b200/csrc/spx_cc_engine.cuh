@@ -49,9 +49,9 @@ static const TwTable<384> h_tw384 = TwTable<384>();
 
 template <int P> SPX_HD cf tw(int k);
 #if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
-#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return cmake(c_tw##P.re[k], c_tw##P.im[k]); }
+#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return c_tw##P.w[k]; }
 #else
-#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return cmake(h_tw##P.re[k], h_tw##P.im[k]); }
+#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return h_tw##P.w[k]; }
 #endif
 SPX_TW(48) SPX_TW(96) SPX_TW(192) SPX_TW(384)
 #undef SPX_TW
@@ -90,6 +90,8 @@ struct PairState {
     unsigned flags;
     float mu, mu_ref;      // ZNCC means (0 otherwise)
     float rscale;          // normalisation folded into R
+    int interior;          // box entirely inside the source image
+    int report;            // status bits of the tiles whose NaN/Inf are reported
     int status;
     Best best;             // running argmax over the interlaced surface
 };
@@ -103,23 +105,38 @@ struct Ctx {
 };
 
 SPX_HD float ld_f32(const float *p) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
     return __ldg(p);
 #else
     return *p;
 #endif
 }
 
-// pixel (y, x) of tile s in cutout coordinates, 0 outside the source image
-// (Cutout 'fill' mode with fillval 0, cutout.py:737-752)
-SPX_HD float load_px(const PairState &ps, int s, int y, int x) {
-    const int yy = y + ps.y0[s], xx = x + ps.x0[s];
-    if (yy < 0 || yy >= ps.H || xx < 0 || xx >= ps.W) return 0.f;
-    return ld_f32(ps.base[s] + (long long)yy * ps.pitch[s] + xx);
-}
-
 // W row r holds frequency ky = r/E2 + E1*(r%E2)  (in-place two-step order)
 template <class C> SPX_HD int ky_of_row(int r) { return r / C::E2 + C::E1 * (r % C::E2); }
+
+SPX_HD unsigned f32_bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+
+// Geometry of one tile column as seen by one lane: pointer to cutout pixel
+// (0, x) and whether that column exists in the source image.  Pixels outside
+// the source image read as 0 (Cutout 'fill' mode, cutout.py:737-752).
+struct TileCol {
+    const float *p;        // address of cutout pixel (y=0, x) - may be out of range
+    long long pitch;
+    bool colok;
+};
+SPX_HD TileCol tile_col(const PairState &ps, int s, int x, bool active) {
+    TileCol t;
+    const int xx = x + ps.x0[s];
+    t.pitch = ps.pitch[s];
+    t.colok = active && (ps.interior || (xx >= 0 && xx < ps.W));
+    t.p = ps.base[s] + (long long)ps.y0[s] * t.pitch + xx;
+    return t;
+}
+SPX_HD bool row_ok(const PairState &ps, int s, int y) {      // y in cutout coords
+    const int yy = y + ps.y0[s];
+    return y >= 0 && y < ps.ny && (ps.interior || (yy >= 0 && yy < ps.H));
+}
 
 // --------------------------------------------------------------------------
 // statistics pre-pass (cc.py:131-156), one thread's share
@@ -136,17 +153,11 @@ SPX_HD void stat_merge(StatPartial &a, const StatPartial &b) {
     a.rcnt += b.rcnt; a.rsum += b.rsum; a.rsq += b.rsq; a.flags |= b.flags;
 }
 
-SPX_HD bool zero_bad(const PairState &ps, int s) {
-    return s == 0 ? (ps.flags & SPX_F_ZERO_BAD_REF) != 0
-                  : (ps.flags & SPX_F_ZERO_BAD_PHASES) != 0;
-}
-
-// fetch + sanitise: non-finite pixels become 0; they raise the tile's status
-// bit unless the caller asked for masked-pixel zeroing (align.py:661)
-SPX_HD float fetch(const PairState &ps, int s, int y, int x, int &flags) {
-    float v = load_px(ps, s, y, x);
-    if (!finitef(v)) {
-        if (!zero_bad(ps, s)) flags |= (SPX_S_NONFINITE_REF << s);
+// non-finite pixels become 0; they raise the tile's status bit unless the
+// caller asked for masked-pixel zeroing (align.py:661)
+SPX_HD float sanitize(float v, int s, int report, int &flags) {
+    if ((f32_bits(v) & 0x7f800000u) == 0x7f800000u) {
+        flags |= report & (SPX_S_NONFINITE_REF << s);
         v = 0.f;
     }
     return v;
@@ -155,22 +166,32 @@ SPX_HD float fetch(const PairState &ps, int s, int y, int x, int &flags) {
 template <class C>
 SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
     StatPartial st = stat_zero();
-    const int npix = ps.ny * ps.nx;
-    for (int idx = tid; idx < npix; idx += C::T) {
-        const int y = idx / ps.nx, x = idx - y * ps.nx;
-        bool any = false;
-        for (int s = 1; s < 5; ++s) {
-            const float v = fetch(ps, s, y, x, st.flags);
-            if (v != 0.f) {                               // cc.py:134-137
-                const double d = double(v);
-                st.cnt += 1.0; st.sum += d; st.sq += d * d;
-                any = true;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ny = ps.ny, nx = ps.nx, report = ps.report;
+    for (int x = lane; x < nx; x += 32) {
+        TileCol tc[5];
+        for (int s = 0; s < 5; ++s) tc[s] = tile_col(ps, s, x, true);
+        for (int y = warp; y < ny; y += C::NW) {
+            const bool ok = row_ok(ps, 0, y);
+            float v[5];
+#pragma unroll
+            for (int s = 0; s < 5; ++s)
+                v[s] = (ok && tc[s].colok) ? ld_f32(tc[s].p + (long long)y * tc[s].pitch) : 0.f;
+            bool any = false;
+#pragma unroll
+            for (int s = 1; s < 5; ++s) {
+                const float q = sanitize(v[s], s, report, st.flags);
+                if (q != 0.f) {                               // cc.py:134-137
+                    const double d = double(q);
+                    st.cnt += 1.0; st.sum += d; st.sq += d * d;
+                    any = true;
+                }
             }
-        }
-        const float r = fetch(ps, 0, y, x, st.flags);
-        if (any) {                                        // cc.py:150-154
-            const double d = double(r);
-            st.rcnt += 1.0; st.rsum += d; st.rsq += d * d;
+            const float r = sanitize(v[0], 0, report, st.flags);
+            if (any) {                                        // cc.py:150-154
+                const double d = double(r);
+                st.rcnt += 1.0; st.rsum += d; st.rsq += d * d;
+            }
         }
     }
     return st;
@@ -212,28 +233,61 @@ template <class C>
 SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
     const PairState &ps = *c.ps;
     const int warp = tid >> 5, lane = tid & 31;
-    const int nchunk = (ps.nx + 31) >> 5;
-    const bool is_ref = (sa == 0);
+    const int nx = ps.nx, report = ps.report;
+    const int nchunk = (nx + 31) >> 5;
+    const bool is_ref = (sa == 0), pair = sb >= 0;
+    const bool zncc = ps.cc_type == SPX_ZNCC;
+    const float mu = ps.mu, mu_ref = ps.mu_ref;
     int flags = 0;
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
-        const bool active = i < ps.nx;
-        cf x[C::E1];
+        const bool active = i < nx;
+        const TileCol ta = tile_col(ps, sa, i, active);
+        const TileCol tb = tile_col(ps, pair ? sb : sa, i, active && pair);
+        const int ybase = n2 - yoff;
+        // all loads first (independent, predicated), arithmetic afterwards
+        float va[C::E1], vb[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
-            const int y = C::E2 * n1 + n2 - yoff;
-            float va = 0.f, vb = 0.f;
-            if (active && y >= 0 && y < ps.ny) {
-                va = fetch(ps, sa, y, i, flags);
-                if (is_ref) va -= ps.mu_ref;                  // cc.py:152-153
-                else if (va != 0.f) va -= ps.mu;              // cc.py:145-146
-                if (sb >= 0) {
-                    vb = fetch(ps, sb, y, i, flags);
-                    if (vb != 0.f) vb -= ps.mu;
-                }
-            }
-            x[n1] = cmake(va, vb);
+            const int y = C::E2 * n1 + ybase;
+            const bool ok = row_ok(ps, sa, y);               // warp-uniform
+            va[n1] = (ok && ta.colok) ? ld_f32(ta.p + (long long)y * ta.pitch) : 0.f;
+            vb[n1] = (ok && tb.colok) ? ld_f32(tb.p + (long long)y * tb.pitch) : 0.f;
         });
+        // one cheap test for "any NaN/Inf among my pixels": max of |bits|
+        unsigned worst = 0u;
+        static_for<0, C::E1>([&](auto N1) {
+            constexpr int n1 = decltype(N1)::value;
+            const unsigned ua = f32_bits(va[n1]) & 0x7fffffffu, ub = f32_bits(vb[n1]) & 0x7fffffffu;
+            worst = worst > ua ? worst : ua;
+            worst = worst > ub ? worst : ub;
+        });
+        if (worst >= 0x7f800000u) {                          // rare
+            static_for<0, C::E1>([&](auto N1) {
+                constexpr int n1 = decltype(N1)::value;
+                va[n1] = sanitize(va[n1], sa, report, flags);
+                vb[n1] = sanitize(vb[n1], pair ? sb : sa, report, flags);
+            });
+        }
+        cf x[C::E1];
+        if (zncc) {
+            static_for<0, C::E1>([&](auto N1) {
+                constexpr int n1 = decltype(N1)::value;
+                const int y = C::E2 * n1 + ybase;
+                float a = va[n1], b = vb[n1];
+                if (is_ref) { if (active && y >= 0 && y < ps.ny) a -= mu_ref; }   // cc.py:152-153
+                else {
+                    if (a != 0.f) a -= mu;                                          // cc.py:145-146
+                    if (b != 0.f) b -= mu;
+                }
+                x[n1] = cmake(a, b);
+            });
+        } else {
+            static_for<0, C::E1>([&](auto N1) {
+                constexpr int n1 = decltype(N1)::value;
+                x[n1] = cmake(va[n1], vb[n1]);
+            });
+        }
         RegFFT<C::E1, false>::run(x);
         if (active) {
             static_for<0, C::E1>([&](auto K1) {
@@ -248,12 +302,12 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
 // C2: E2-point FFT over n2 for every (column, k1), in place.
 template <class C>
 SPX_HD void c2_pass(const Ctx<C> &c, int tid) {
-    const PairState &ps = *c.ps;
     const int warp = tid >> 5, lane = tid & 31;
-    const int nchunk = (ps.nx + 31) >> 5;
+    const int nx = c.ps->nx;
+    const int nchunk = (nx + 31) >> 5;
     for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
         const int k1 = wi % C::E1, i = (wi / C::E1) * 32 + lane;
-        if (i >= ps.nx) continue;
+        if (i >= nx) continue;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
@@ -270,12 +324,12 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid) {
 // IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
 template <class C>
 SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
-    const PairState &ps = *c.ps;
     const int warp = tid >> 5, lane = tid & 31;
-    const int nchunk = (ps.nx + 31) >> 5;
+    const int nx = c.ps->nx;
+    const int nchunk = (nx + 31) >> 5;
     for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
         const int k1 = wi % C::E1, l = (wi / C::E1) * 32 + lane;
-        if (l >= ps.nx) continue;
+        if (l >= nx) continue;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
@@ -291,37 +345,42 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
 
 // IC2: E1-point inverse FFT over k1; outputs n = E2*n1+n2 < ny are the lags
 // n - yc of phases (a=0, b) [real part] and (a=1, b) [imaginary part].
+// Inputs were sanitised, so the surface is finite and a plain ">" scan in
+// increasing index order implements numpy's first-maximum rule per item.
 template <class C>
 SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
     const PairState &ps = *c.ps;
     const int warp = tid >> 5, lane = tid & 31;
-    const int nchunk = (ps.nx + 31) >> 5;
+    const int ny = ps.ny, nx = ps.nx;
+    const int nchunk = (nx + 31) >> 5;
     const float norm = 1.0f / (float(C::P) * float(C::P));
-    const int w2 = 2 * ps.nx;
+    const int w2 = 2 * nx;
+    float *icc = c.icc;
     Best best = best_init();
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, l = (wi / C::E2) * 32 + lane;
-        if (l >= ps.nx) continue;
+        if (l >= nx) continue;
         cf x[C::E1];
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
             x[k1] = c.W[(k1 * C::E2 + n2) * C::WP + l];
         });
         RegFFT<C::E1, true>::run(x);
+        const int idx0 = (2 * n2 + b) * w2 + 2 * l;
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
-            const int n = C::E2 * n1 + n2;
-            if (n < ps.ny) {
+            if (C::E2 * n1 + n2 < ny) {
                 const float v0 = x[n1].x * norm, v1 = x[n1].y * norm;
-                const int idx = (2 * n + b) * w2 + 2 * l;
-                cf o = cmake(v0, v1);
-                *reinterpret_cast<cf *>(c.icc + idx) = o;
-                Best c0; c0.v = v0; c0.idx = idx;
-                Best c1; c1.v = v1; c1.idx = idx + 1;
-                if (best_better(c0, best)) best = c0;
-                if (best_better(c1, best)) best = c1;
+                const int idx = idx0 + n1 * (2 * C::E2) * w2;
+                *reinterpret_cast<cf *>(icc + idx) = cmake(v0, v1);
+                if (v0 > bv) { bv = v0; bi = idx; }
+                if (v1 > bv) { bv = v1; bi = idx + 1; }
             }
         });
+        Best cand; cand.v = bv; cand.idx = bi;
+        if (best_better(cand, best)) best = cand;
     }
     return best;
 }
@@ -332,14 +391,15 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
 // X1: r = W row handled by this lane (or -1), xoff = column offset of the tile
 template <class C>
 SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
-    const PairState &ps = *c.ps;
     const int warp = tid >> 5, lane = tid & 31;
+    const int nx = c.ps->nx;
+    const cf *Wrow = c.W + (r >= 0 ? r : 0) * C::WP - xoff;
     for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
         cf x[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             const int i = C::E2 * n1 + n2 - xoff;
-            x[n1] = (r >= 0 && i >= 0 && i < ps.nx) ? c.W[r * C::WP + i] : cmake(0.f, 0.f);
+            x[n1] = (r >= 0 && i >= 0 && i < nx) ? Wrow[C::E2 * n1 + n2] : cmake(0.f, 0.f);
         });
         RegFFT<C::E1, false>::run(x);
         static_for<0, C::E1>([&](auto K1) {
@@ -353,9 +413,8 @@ SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
 // conj(R) * rscale for ky <= P/2.
 template <class C>
 SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int ky) {
-    const PairState &ps = *c.ps;
     const int warp = tid >> 5, lane = tid & 31;
-    const float sc = ps.rscale;
+    const float sc = c.ps->rscale;
     for (int k1 = warp; k1 < C::E1; k1 += C::NW) {
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
@@ -386,13 +445,15 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
             x[n2] = c.S[lane * C::SP + k1 * C::E2 + n2];
         });
         RegFFT<C::E2, false>::run(x);
+        // column of kx = k1 + E1*k2 is k1*E2 + k2; the mirrored frequency
+        // (P - kx) % P sits at (E1-k1)*E2 + (E2-1-k2) for k1 > 0 and at
+        // (E2-k2) % E2 for k1 == 0  (all warp-uniform)
+        const int col_d = k1 * C::E2;
+        const int col_f = k1 ? (C::E1 - k1) * C::E2 + C::E2 - 1 : C::E2;
+        const cf *Rd = Rrow + (flip ? col_f : col_d);
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            const int kx = k1 + C::E1 * k2;                 // warp-uniform
-            const int kxm = (C::P - kx) % C::P;
-            const int col_d = k1 * C::E2 + k2;
-            const int col_f = (kxm % C::E1) * C::E2 + kxm / C::E1;
-            cf v = Rrow[flip ? col_f : col_d];
+            cf v = flip ? ((k1 == 0 && k2 == 0) ? Rrow[0] : Rd[-k2]) : Rd[k2];
             if (flip) v.y = -v.y;   // conj(R[ky,kx]) = R[P-ky,P-kx]; storage holds conj(R)
             x[k2] = cmul(x[k2], v);
         });
@@ -407,8 +468,8 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
 // X3: E1-point inverse FFT over k1, keep samples m = E2*n1+n2 < nx
 template <class C>
 SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r) {
-    const PairState &ps = *c.ps;
     const int warp = tid >> 5, lane = tid & 31;
+    const int nx = c.ps->nx;
     for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
         cf x[C::E1];
         static_for<0, C::E1>([&](auto K1) {
@@ -420,7 +481,7 @@ SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r) {
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
                 const int m = C::E2 * n1 + n2;
-                if (m < ps.nx) c.W[r * C::WP + m] = x[n1];
+                if (m < nx) c.W[r * C::WP + m] = x[n1];
             });
         }
     }
@@ -515,6 +576,12 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
         ps->yc = (job.ny - 1) / 2; ps->xc = (job.nx - 1) / 2;
         ps->cc_type = job.cc_type; ps->flags = job.flags;
         ps->mu = 0.f; ps->mu_ref = 0.f; ps->rscale = 1.f;
+        ps->interior = job.x1 >= 0 && job.y1 >= 0 && job.x1 + job.nx <= job.W &&
+                       job.y1 + job.ny <= job.H;
+        ps->report = ((job.flags & SPX_F_ZERO_BAD_REF) ? 0 : SPX_S_NONFINITE_REF) |
+                     ((job.flags & SPX_F_ZERO_BAD_PHASES) ? 0 :
+                      (SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 | SPX_S_NONFINITE_P01 |
+                       SPX_S_NONFINITE_P11));
         ps->status = job.status0;
         ps->best = best_init();
     });

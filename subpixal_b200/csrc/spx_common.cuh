@@ -10,6 +10,7 @@
 #define __host__
 #define __device__
 #define __forceinline__ inline
+#define __align__(n) __attribute__((aligned(n)))
 #else
 #include <cuda_runtime.h>
 #endif
@@ -68,7 +69,7 @@ __host__ __device__ constexpr double sin2pi(long long k, long long n) {
 }
 
 // ---- complex helpers ------------------------------------------------------
-struct cf { float x, y; };     // plain complex float (same layout as float2)
+struct __align__(8) cf { float x, y; };   // plain complex float (float2 layout)
 
 SPX_HD cf cmake(float a, float b) { cf r; r.x = a; r.y = b; return r; }
 SPX_HD cf cadd(cf a, cf b) { return cmake(a.x + b.x, a.y + b.y); }
@@ -84,11 +85,11 @@ SPX_HD cf cconj(cf a) { return cmake(a.x, -a.y); }
 // ---- twiddle tables W_P^k = exp(-2*pi*i*k/P), k in [0, P) ---------------
 template <int P>
 struct TwTable {
-    float re[P], im[P];
-    constexpr TwTable() : re(), im() {
+    cf w[P];
+    constexpr TwTable() : w() {
         for (int k = 0; k < P; ++k) {
-            re[k] = float(cos2pi(k, P));
-            im[k] = float(-sin2pi(k, P));
+            w[k].x = float(cos2pi(k, P));
+            w[k].y = float(-sin2pi(k, P));
         }
     }
 };

@@ -122,6 +122,30 @@ struct DevExec {
     __device__ __forceinline__ float load_icc(const float *p) { return __ldcg(p); }
 };
 
+// Pull the five tiles of a (future) pair into L2 so that its loads do not pay
+// the HBM latency: one prefetch per 128-byte line, spread over the CTA.
+template <class C>
+__device__ __forceinline__ void prefetch_pair(const CcParams &prm, int p) {
+    if (p >= prm.n) return;
+    int x1 = 0, y1 = 0;
+    if (prm.boxes) {
+        const int4 b = __ldg(reinterpret_cast<const int4 *>(prm.boxes) + p);
+        x1 = b.x; y1 = b.y;
+    }
+    const int segs = (prm.nx + 31) / 32 + 1;             // 128-byte segments per row (unaligned start)
+    const int per_tile = prm.ny * segs;
+    for (int t = threadIdx.x; t < 5 * per_tile; t += C::T) {
+        const int s = t / per_tile, rem = t - s * per_tile;
+        const int row = rem / segs, seg = rem - row * segs;
+        const int yy = y1 + row;
+        int xx = x1 + seg * 32;
+        if (xx > x1 + prm.nx - 1) xx = x1 + prm.nx - 1;
+        if (yy < 0 || yy >= prm.H || xx < 0 || xx >= prm.W) continue;
+        const float *ptr = prm.src[s] + size_t(p) * prm.pair_stride[s] + (long long)yy * prm.pitch + xx;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams prm) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -160,6 +184,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
         job.pitch = prm.pitch; job.H = prm.H; job.W = prm.W;
         job.ny = prm.ny; job.nx = prm.nx; job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
+        prefetch_pair<C>(prm, p + gridDim.x);
         process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
     }
 }
@@ -287,6 +312,7 @@ int spx_cc_fit_frames(const float *const frames_host[5],
                       void *stream) {
     if (!frames_host || !boxes || frame_h < 1 || frame_w < 1 || frame_pitch < frame_w)
         return SPX_E_BADARG;
+    if (int64_t(frame_h) * frame_pitch >= (int64_t(1) << 31)) return SPX_E_UNSUPPORTED;
     spx::CcParams prm{};
     for (int s = 0; s < 5; ++s) { prm.src[s] = frames_host[s]; prm.pair_stride[s] = 0; }
     prm.pitch = frame_pitch; prm.H = frame_h; prm.W = frame_w;

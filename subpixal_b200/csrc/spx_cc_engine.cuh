@@ -90,6 +90,7 @@ struct PairState {
     unsigned flags;
     float mu, mu_ref;      // ZNCC means (0 otherwise)
     float rscale;          // normalisation folded into R
+    int ylo, yhi, xlo, xhi; // cutout rows/cols that exist in the source image
     int interior;          // box entirely inside the source image
     int report;            // status bits of the tiles whose NaN/Inf are reported
     int status;
@@ -103,6 +104,17 @@ struct Ctx {
     const uint16_t *rrow;  // rows of W (scrambled ky order) with ky <= P/2
     PairState *ps;
 };
+
+// Warp index as a value the compiler KNOWS is warp-uniform (so that n2 / k1,
+// the predicates and the twiddle addresses derived from it live in uniform
+// registers): broadcast lane 0's copy.
+SPX_HD int warp_of(int tid) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    return __shfl_sync(0xffffffffu, tid >> 5, 0);
+#else
+    return tid >> 5;
+#endif
+}
 
 SPX_HD float ld_f32(const float *p) {
 #if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
@@ -122,20 +134,15 @@ SPX_HD unsigned f32_bits(float v) { union { float f; unsigned u; } c; c.f = v; r
 // the source image read as 0 (Cutout 'fill' mode, cutout.py:737-752).
 struct TileCol {
     const float *p;        // address of cutout pixel (y=0, x) - may be out of range
-    long long pitch;
+    int pitch;
     bool colok;
 };
 SPX_HD TileCol tile_col(const PairState &ps, int s, int x, bool active) {
     TileCol t;
-    const int xx = x + ps.x0[s];
-    t.pitch = ps.pitch[s];
-    t.colok = active && (ps.interior || (xx >= 0 && xx < ps.W));
-    t.p = ps.base[s] + (long long)ps.y0[s] * t.pitch + xx;
+    t.pitch = int(ps.pitch[s]);
+    t.colok = active && x >= ps.xlo && x < ps.xhi;
+    t.p = ps.base[s] + ((long long)ps.y0[s] * t.pitch + (x + ps.x0[s]));
     return t;
-}
-SPX_HD bool row_ok(const PairState &ps, int s, int y) {      // y in cutout coords
-    const int yy = y + ps.y0[s];
-    return y >= 0 && y < ps.ny && (ps.interior || (yy >= 0 && yy < ps.H));
 }
 
 // --------------------------------------------------------------------------
@@ -166,32 +173,31 @@ SPX_HD float sanitize(float v, int s, int report, int &flags) {
 template <class C>
 SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
     StatPartial st = stat_zero();
-    const int warp = tid >> 5, lane = tid & 31;
-    const int ny = ps.ny, nx = ps.nx, report = ps.report;
+    const int warp = warp_of(tid), lane = tid & 31;
+    const int nx = ps.nx, report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
     for (int x = lane; x < nx; x += 32) {
         TileCol tc[5];
+#pragma unroll
         for (int s = 0; s < 5; ++s) tc[s] = tile_col(ps, s, x, true);
-        for (int y = warp; y < ny; y += C::NW) {
-            const bool ok = row_ok(ps, 0, y);
+        // rows outside [ylo, yhi) are fill pixels: zero in every tile, so they
+        // contribute to no sum (cc.py:134-137 masks zeros)
+        for (int y = ylo + warp; y < yhi; y += C::NW) {
             float v[5];
 #pragma unroll
             for (int s = 0; s < 5; ++s)
-                v[s] = (ok && tc[s].colok) ? ld_f32(tc[s].p + (long long)y * tc[s].pitch) : 0.f;
+                v[s] = tc[s].colok ? ld_f32(tc[s].p + y * tc[s].pitch) : 0.f;
             bool any = false;
 #pragma unroll
             for (int s = 1; s < 5; ++s) {
                 const float q = sanitize(v[s], s, report, st.flags);
-                if (q != 0.f) {                               // cc.py:134-137
-                    const double d = double(q);
-                    st.cnt += 1.0; st.sum += d; st.sq += d * d;
-                    any = true;
-                }
+                const bool nz = q != 0.f;                     // cc.py:134-137
+                const double d = double(q);
+                st.cnt += nz ? 1.0 : 0.0; st.sum += d; st.sq += d * d;
+                any |= nz;
             }
             const float r = sanitize(v[0], 0, report, st.flags);
-            if (any) {                                        // cc.py:150-154
-                const double d = double(r);
-                st.rcnt += 1.0; st.rsum += d; st.rsq += d * d;
-            }
+            const double d = any ? double(r) : 0.0;           // cc.py:150-154
+            st.rcnt += any ? 1.0 : 0.0; st.rsum += d; st.rsq += d * d;
         }
     }
     return st;
@@ -232,8 +238,8 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
 template <class C>
 SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
     const PairState &ps = *c.ps;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nx = ps.nx, report = ps.report;
+    const int warp = warp_of(tid), lane = tid & 31;
+    const int nx = ps.nx, ny = ps.ny, report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
     const int nchunk = (nx + 31) >> 5;
     const bool is_ref = (sa == 0), pair = sb >= 0;
     const bool zncc = ps.cc_type == SPX_ZNCC;
@@ -245,14 +251,17 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
         const TileCol ta = tile_col(ps, sa, i, active);
         const TileCol tb = tile_col(ps, pair ? sb : sa, i, active && pair);
         const int ybase = n2 - yoff;
+        const int rs = C::E2 * ta.pitch;                     // elements between loads
+        const float *pa0 = ta.p + ybase * ta.pitch;
+        const float *pb0 = tb.p + ybase * tb.pitch;
         // all loads first (independent, predicated), arithmetic afterwards
         float va[C::E1], vb[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             const int y = C::E2 * n1 + ybase;
-            const bool ok = row_ok(ps, sa, y);               // warp-uniform
-            va[n1] = (ok && ta.colok) ? ld_f32(ta.p + (long long)y * ta.pitch) : 0.f;
-            vb[n1] = (ok && tb.colok) ? ld_f32(tb.p + (long long)y * tb.pitch) : 0.f;
+            const bool ok = y >= ylo && y < yhi;             // warp-uniform
+            va[n1] = (ok && ta.colok) ? ld_f32(pa0 + n1 * rs) : 0.f;
+            vb[n1] = (ok && tb.colok) ? ld_f32(pb0 + n1 * rs) : 0.f;
         });
         // one cheap test for "any NaN/Inf among my pixels": max of |bits|
         unsigned worst = 0u;
@@ -275,7 +284,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
                 constexpr int n1 = decltype(N1)::value;
                 const int y = C::E2 * n1 + ybase;
                 float a = va[n1], b = vb[n1];
-                if (is_ref) { if (active && y >= 0 && y < ps.ny) a -= mu_ref; }   // cc.py:152-153
+                if (is_ref) { if (active && y >= 0 && y < ny) a -= mu_ref; }   // cc.py:152-153
                 else {
                     if (a != 0.f) a -= mu;                                          // cc.py:145-146
                     if (b != 0.f) b -= mu;
@@ -302,7 +311,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
 // C2: E2-point FFT over n2 for every (column, k1), in place.
 template <class C>
 SPX_HD void c2_pass(const Ctx<C> &c, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
     for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
@@ -324,7 +333,7 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid) {
 // IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
 template <class C>
 SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
     for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
@@ -350,7 +359,7 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
 template <class C>
 SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
     const PairState &ps = *c.ps;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = warp_of(tid), lane = tid & 31;
     const int ny = ps.ny, nx = ps.nx;
     const int nchunk = (nx + 31) >> 5;
     const float norm = 1.0f / (float(C::P) * float(C::P));
@@ -391,7 +400,7 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
 // X1: r = W row handled by this lane (or -1), xoff = column offset of the tile
 template <class C>
 SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     const cf *Wrow = c.W + (r >= 0 ? r : 0) * C::WP - xoff;
     for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
@@ -413,7 +422,7 @@ SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
 // conj(R) * rscale for ky <= P/2.
 template <class C>
 SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int ky) {
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = warp_of(tid), lane = tid & 31;
     const float sc = c.ps->rscale;
     for (int k1 = warp; k1 < C::E1; k1 += C::NW) {
         cf x[C::E2];
@@ -434,7 +443,7 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int ky) {
 // X2: forward E2-FFT, multiply by conj(R[ky, kx]), inverse E2-FFT (+twiddle)
 template <class C>
 SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = warp_of(tid), lane = tid & 31;
     const int ky = r >= 0 ? ky_of_row<C>(r) : 0;
     const bool flip = ky > C::P / 2;
     const cf *Rrow = c.R + (flip ? C::P - ky : ky) * C::RP;
@@ -468,7 +477,7 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
 // X3: E1-point inverse FFT over k1, keep samples m = E2*n1+n2 < nx
 template <class C>
 SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r) {
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
         cf x[C::E1];
@@ -576,6 +585,10 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
         ps->yc = (job.ny - 1) / 2; ps->xc = (job.nx - 1) / 2;
         ps->cc_type = job.cc_type; ps->flags = job.flags;
         ps->mu = 0.f; ps->mu_ref = 0.f; ps->rscale = 1.f;
+        ps->ylo = job.y1 < 0 ? -job.y1 : 0;
+        ps->yhi = job.y1 + job.ny > job.H ? job.H - job.y1 : job.ny;
+        ps->xlo = job.x1 < 0 ? -job.x1 : 0;
+        ps->xhi = job.x1 + job.nx > job.W ? job.W - job.x1 : job.nx;
         ps->interior = job.x1 >= 0 && job.y1 >= 0 && job.x1 + job.nx <= job.W &&
                        job.y1 + job.ny <= job.H;
         ps->report = ((job.flags & SPX_F_ZERO_BAD_REF) ? 0 : SPX_S_NONFINITE_REF) |

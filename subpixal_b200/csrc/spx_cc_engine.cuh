@@ -235,41 +235,60 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
 // --------------------------------------------------------------------------
 // C1: tiles (sa -> real part, sb -> imaginary part, sb < 0: none) placed at
 // row offset yoff; E1-point FFT over n1 for every (column i, n2).
-template <class C>
+//
+// FAST = full-size (ny = nx = NMAX) cutout lying entirely inside the source
+// image.  The image tiles are then placed at offset NMAX/2 (a multiple of E2)
+// instead of (n-1)/2, which makes the zero-padding pattern a compile-time
+// property of n1: reference rows exist for n1 < NMAX/E2, image rows for
+// n1 >= NMAX/(2*E2).  No bounds tests, no predicates, minimal address math.
+template <class C, bool FAST, bool IS_REF>
 SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = ps.nx, ny = ps.ny, report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
+    const int nx = FAST ? C::NMAX : ps.nx, ny = FAST ? C::NMAX : ps.ny;
+    const int report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
     const int nchunk = (nx + 31) >> 5;
-    const bool is_ref = (sa == 0), pair = sb >= 0;
+    const bool pair = !IS_REF;
     const bool zncc = ps.cc_type == SPX_ZNCC;
     const float mu = ps.mu, mu_ref = ps.mu_ref;
+    constexpr int N1_LO = (FAST && !IS_REF) ? C::NMAX / (2 * C::E2) : 0;
+    constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
+    static_assert(!FAST || (C::NMAX / 2) % C::E2 == 0, "fast path needs E2 | NMAX/2");
     int flags = 0;
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
-        const bool active = i < nx;
+        const bool active = FAST || i < nx;
         const TileCol ta = tile_col(ps, sa, i, active);
         const TileCol tb = tile_col(ps, pair ? sb : sa, i, active && pair);
         const int ybase = n2 - yoff;
         const int rs = C::E2 * ta.pitch;                     // elements between loads
         const float *pa0 = ta.p + ybase * ta.pitch;
         const float *pb0 = tb.p + ybase * tb.pitch;
-        // all loads first (independent, predicated), arithmetic afterwards
+        // all loads first (independent), arithmetic afterwards
         float va[C::E1], vb[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
-            const int y = C::E2 * n1 + ybase;
-            const bool ok = y >= ylo && y < yhi;             // warp-uniform
-            va[n1] = (ok && ta.colok) ? ld_f32(pa0 + n1 * rs) : 0.f;
-            vb[n1] = (ok && tb.colok) ? ld_f32(pb0 + n1 * rs) : 0.f;
+            if constexpr (FAST) {
+                if constexpr (n1 >= N1_LO && n1 < N1_HI) {
+                    va[n1] = ld_f32(pa0 + n1 * rs);
+                    vb[n1] = pair ? ld_f32(pb0 + n1 * rs) : 0.f;
+                } else {
+                    va[n1] = 0.f; vb[n1] = 0.f;
+                }
+            } else {
+                const int y = C::E2 * n1 + ybase;
+                const bool ok = y >= ylo && y < yhi;         // warp-uniform
+                va[n1] = (ok && ta.colok) ? ld_f32(pa0 + n1 * rs) : 0.f;
+                vb[n1] = (ok && tb.colok) ? ld_f32(pb0 + n1 * rs) : 0.f;
+            }
         });
         // one cheap test for "any NaN/Inf among my pixels": max of |bits|
         unsigned worst = 0u;
-        static_for<0, C::E1>([&](auto N1) {
+        static_for<N1_LO, N1_HI>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             const unsigned ua = f32_bits(va[n1]) & 0x7fffffffu, ub = f32_bits(vb[n1]) & 0x7fffffffu;
             worst = worst > ua ? worst : ua;
-            worst = worst > ub ? worst : ub;
+            if (pair) worst = worst > ub ? worst : ub;
         });
         if (worst >= 0x7f800000u) {                          // rare
             static_for<0, C::E1>([&](auto N1) {
@@ -284,7 +303,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
                 constexpr int n1 = decltype(N1)::value;
                 const int y = C::E2 * n1 + ybase;
                 float a = va[n1], b = vb[n1];
-                if (is_ref) { if (active && y >= 0 && y < ny) a -= mu_ref; }   // cc.py:152-153
+                if (IS_REF) { if (active && y >= 0 && y < ny) a -= mu_ref; }      // cc.py:152-153
                 else {
                     if (a != 0.f) a -= mu;                                          // cc.py:145-146
                     if (b != 0.f) b -= mu;
@@ -357,7 +376,7 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
 // Inputs were sanitised, so the surface is finite and a plain ">" scan in
 // increasing index order implements numpy's first-maximum rule per item.
 template <class C>
-SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
+SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int ny = ps.ny, nx = ps.nx;
@@ -375,12 +394,14 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
             x[k1] = c.W[(k1 * C::E2 + n2) * C::WP + l];
         });
         RegFFT<C::E1, true>::run(x);
-        const int idx0 = (2 * n2 + b) * w2 + 2 * l;
+        // sample n = E2*n1 + n2 is lag (n - shift) - yc -> surface row 2*(n-shift)+b
+        const int nb = n2 - shift;
+        const int idx0 = (2 * nb + b) * w2 + 2 * l;
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
-            if (C::E2 * n1 + n2 < ny) {
+            if (unsigned(C::E2 * n1 + nb) < unsigned(ny)) {
                 const float v0 = x[n1].x * norm, v1 = x[n1].y * norm;
                 const int idx = idx0 + n1 * (2 * C::E2) * w2;
                 *reinterpret_cast<cf *>(icc + idx) = cmake(v0, v1);
@@ -398,17 +419,26 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b) {
 // row passes on one batch of 32 rows; lane <-> row
 // --------------------------------------------------------------------------
 // X1: r = W row handled by this lane (or -1), xoff = column offset of the tile
-template <class C>
+template <class C, bool FAST, bool IS_REF>
 SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = c.ps->nx;
+    const int nx = FAST ? C::NMAX : c.ps->nx;
     const cf *Wrow = c.W + (r >= 0 ? r : 0) * C::WP - xoff;
+    constexpr int N1_LO = (FAST && !IS_REF) ? C::NMAX / (2 * C::E2) : 0;
+    constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
     for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
         cf x[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
-            const int i = C::E2 * n1 + n2 - xoff;
-            x[n1] = (r >= 0 && i >= 0 && i < nx) ? Wrow[C::E2 * n1 + n2] : cmake(0.f, 0.f);
+            if constexpr (FAST) {
+                if constexpr (n1 >= N1_LO && n1 < N1_HI)
+                    x[n1] = (IS_REF && r < 0) ? cmake(0.f, 0.f) : Wrow[C::E2 * n1 + n2];
+                else
+                    x[n1] = cmake(0.f, 0.f);
+            } else {
+                const int i = C::E2 * n1 + n2 - xoff;
+                x[n1] = (r >= 0 && i >= 0 && i < nx) ? Wrow[C::E2 * n1 + n2] : cmake(0.f, 0.f);
+            }
         });
         RegFFT<C::E1, false>::run(x);
         static_for<0, C::E1>([&](auto K1) {
@@ -476,7 +506,7 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
 
 // X3: E1-point inverse FFT over k1, keep samples m = E2*n1+n2 < nx
 template <class C>
-SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r) {
+SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r, int shift) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
@@ -489,8 +519,8 @@ SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r) {
         if (r >= 0) {
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
-                const int m = C::E2 * n1 + n2;
-                if (m < nx) c.W[r * C::WP + m] = x[n1];
+                const int m = C::E2 * n1 + n2 - shift;      // lag m - xc
+                if (unsigned(m) < unsigned(nx)) c.W[r * C::WP + m] = x[n1];
             });
         }
     }
@@ -553,6 +583,61 @@ SPX_HD bool icc_is_nan(const PairState &ps, int status, int idx) {
 }
 
 // --------------------------------------------------------------------------
+// reference transform + the two phase pairs (see the data flow at the top)
+// --------------------------------------------------------------------------
+template <class C, bool FAST, class Ex>
+SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
+    PairState *ps = c.ps;
+    // placement offset of the image tiles and the resulting index shift of the
+    // wanted lags: sample m of the circular correlation is lag (m - off)
+    const int yoff = FAST ? C::NMAX / 2 : ps->yc, xoff = FAST ? C::NMAX / 2 : ps->xc;
+    const int ysh = yoff - ps->yc, xsh = xoff - ps->xc;
+
+    // ---- reference image -> conj(R) * scale, half spectrum ---------------
+    ex.par([&](int tid) {
+        const int fl = c1_pass<C, FAST, true>(c, tid, 0, -1, 0);
+        if (fl) ex.or_status(&ps->status, fl);
+    });
+    ex.par([&](int tid) { c2_pass<C>(c, tid); });
+    for (int b0 = 0; b0 < C::RH; b0 += 32) {
+        ex.par([&](int tid) {
+            const int k = b0 + (tid & 31);
+            x1_pass<C, FAST, true>(c, tid, k < C::RH ? int(c.rrow[k]) : -1, 0);
+        });
+        ex.par([&](int tid) {
+            const int k = b0 + (tid & 31);
+            x2_ref_pass<C>(c, tid, k < C::RH ? ky_of_row<C>(int(c.rrow[k])) : -1);
+        });
+    }
+
+    // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
+    for (int b = 0; b < 2; ++b) {
+        ex.par([&](int tid) {
+            const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff);
+            if (fl) ex.or_status(&ps->status, fl);
+        });
+        ex.par([&](int tid) { c2_pass<C>(c, tid); });
+        for (int b0 = 0; b0 < C::P; b0 += 32) {
+            ex.par([&](int tid) {
+                const int r = b0 + (tid & 31);
+                x1_pass<C, FAST, false>(c, tid, r < C::P ? r : -1, xoff);
+            });
+            ex.par([&](int tid) {
+                const int r = b0 + (tid & 31);
+                x2_pass<C>(c, tid, r < C::P ? r : -1);
+            });
+            ex.par([&](int tid) {
+                const int r = b0 + (tid & 31);
+                x3_pass<C>(c, tid, r < C::P ? r : -1, xsh);
+            });
+        }
+        ex.par([&](int tid) { ic1_pass<C>(c, tid); });
+        Best bb = ex.reduce_best([&](int tid) { return ic2_pass<C>(c, tid, b, ysh); });
+        ex.single([&]() { if (best_better(bb, ps->best)) ps->best = bb; });
+    }
+}
+
+// --------------------------------------------------------------------------
 // The pass sequence for ONE pair.  `Ex` supplies the execution model:
 //   par(f)          run f(tid) for every thread of the CTA, then barrier
 //   single(f)       run f() on one thread, then barrier
@@ -605,48 +690,10 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
         ex.single([&]() { stats_finalize(*ps, tot); });
     }
 
-    // ---- reference image -> conj(R) * scale, half spectrum ---------------
-    ex.par([&](int tid) {
-        const int fl = c1_pass<C>(c, tid, 0, -1, 0);
-        if (fl) ex.or_status(&ps->status, fl);
-    });
-    ex.par([&](int tid) { c2_pass<C>(c, tid); });
-    for (int b0 = 0; b0 < C::RH; b0 += 32) {
-        ex.par([&](int tid) {
-            const int k = b0 + (tid & 31);
-            x1_pass<C>(c, tid, k < C::RH ? int(c.rrow[k]) : -1, 0);
-        });
-        ex.par([&](int tid) {
-            const int k = b0 + (tid & 31);
-            x2_ref_pass<C>(c, tid, k < C::RH ? ky_of_row<C>(int(c.rrow[k])) : -1);
-        });
-    }
-
-    // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
-    for (int b = 0; b < 2; ++b) {
-        ex.par([&](int tid) {
-            const int fl = c1_pass<C>(c, tid, 1 + 2 * b, 2 + 2 * b, ps->yc);
-            if (fl) ex.or_status(&ps->status, fl);
-        });
-        ex.par([&](int tid) { c2_pass<C>(c, tid); });
-        for (int b0 = 0; b0 < C::P; b0 += 32) {
-            ex.par([&](int tid) {
-                const int r = b0 + (tid & 31);
-                x1_pass<C>(c, tid, r < C::P ? r : -1, ps->xc);
-            });
-            ex.par([&](int tid) {
-                const int r = b0 + (tid & 31);
-                x2_pass<C>(c, tid, r < C::P ? r : -1);
-            });
-            ex.par([&](int tid) {
-                const int r = b0 + (tid & 31);
-                x3_pass<C>(c, tid, r < C::P ? r : -1);
-            });
-        }
-        ex.par([&](int tid) { ic1_pass<C>(c, tid); });
-        Best bb = ex.reduce_best([&](int tid) { return ic2_pass<C>(c, tid, b); });
-        ex.single([&]() { if (best_better(bb, ps->best)) ps->best = bb; });
-    }
+    const bool fast = job.ny == C::NMAX && job.nx == C::NMAX && job.x1 >= 0 && job.y1 >= 0 &&
+                      job.x1 + job.nx <= job.W && job.y1 + job.ny <= job.H;
+    if (fast) run_transforms<C, true>(c, ex);
+    else run_transforms<C, false>(c, ex);
 
     // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
     ex.single([&]() {

@@ -102,21 +102,40 @@ struct DevExec {
         }
         return tot;
     }
-    template <class F> __device__ __forceinline__ Best reduce_best(F f) {
+    template <class F> __device__ __forceinline__ void parts(int n, F f) {
+        if (int(threadIdx.x) < n) f(int(threadIdx.x));
+        __syncthreads();
+    }
+    template <class F> __device__ __forceinline__ void reduce_best_into(Best *dst, F f) {
         Best b = warp_best(f(int(threadIdx.x)));
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         float *redf = reinterpret_cast<float *>(red);
         int *redi = reinterpret_cast<int *>(red) + 64;
         if (lane == 0) { redf[warp] = b.v; redi[warp] = b.idx; }
         __syncthreads();
-        Best g = best_init();
-        if (threadIdx.x == 0) {
-            for (int w = 0; w < C::NW; ++w) {
-                Best t; t.v = redf[w]; t.idx = redi[w];
-                if (best_better(t, g)) g = t;
-            }
+        if (threadIdx.x < 32) {
+            Best t = best_init();
+            if (lane < C::NW) { t.v = redf[lane]; t.idx = redi[lane]; }
+            t = warp_best(t);
+            if (lane == 0 && best_better(t, *dst)) *dst = t;
         }
-        return g;
+        __syncthreads();
+    }
+    template <class LF, class FF> __device__ __forceinline__ void warp_fit(LF lane_f, FF final_f) {
+        if (threadIdx.x < 32) {
+            FitSums f = lane_f(int(threadIdx.x));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                f.s0 += __shfl_xor_sync(0xffffffffu, f.s0, o);
+                f.su += __shfl_xor_sync(0xffffffffu, f.su, o);
+                f.sv += __shfl_xor_sync(0xffffffffu, f.sv, o);
+                f.suv += __shfl_xor_sync(0xffffffffu, f.suv, o);
+                f.suu += __shfl_xor_sync(0xffffffffu, f.suu, o);
+                f.svv += __shfl_xor_sync(0xffffffffu, f.svv, o);
+            }
+            if (threadIdx.x == 0) final_f(f);
+        }
+        __syncthreads();
     }
     __device__ __forceinline__ void or_status(int *p, int v) { atomicOr(p, v); }
     __device__ __forceinline__ float load_icc(const float *p) { return __ldcg(p); }

@@ -381,7 +381,6 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int ny = ps.ny, nx = ps.nx;
     const int nchunk = (nx + 31) >> 5;
-    const float norm = 1.0f / (float(C::P) * float(C::P));
     const int w2 = 2 * nx;
     float *icc = c.icc;
     Best best = best_init();
@@ -402,7 +401,7 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift) {
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             if (unsigned(C::E2 * n1 + nb) < unsigned(ny)) {
-                const float v0 = x[n1].x * norm, v1 = x[n1].y * norm;
+                const float v0 = x[n1].x, v1 = x[n1].y;
                 const int idx = idx0 + n1 * (2 * C::E2) * w2;
                 *reinterpret_cast<cf *>(icc + idx) = cmake(v0, v1);
                 if (v0 > bv) { bv = v0; bi = idx; }
@@ -453,7 +452,8 @@ SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
 template <class C>
 SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int ky) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const float sc = c.ps->rscale;
+    // normalisation scale and the 1/P^2 of the unnormalised inverse FFTs
+    const float sc = c.ps->rscale * (1.0f / (float(C::P) * float(C::P)));
     for (int k1 = warp; k1 < C::E1; k1 += C::NW) {
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
@@ -527,44 +527,88 @@ SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r, int shift) {
 }
 
 // --------------------------------------------------------------------------
-// peak stage (one thread): numpy.argmax semantics incl. NaN lattices, then
+// peak stage: numpy.argmax semantics incl. NaN lattices, then
 // centroid.find_peak with peak_fit_box=5 (cc.py:86) and cc.py:89-93.
+// The surface is at least 6x6, so the fit box is always a full 5x5 box
+// (centroid.py:165-184) and the least-squares solution has the closed form
+// of SURVEY.md section 3.5.  25 lanes fetch one sample each, the six moment
+// sums are reduced across the warp, one lane finishes.
 // --------------------------------------------------------------------------
-template <class LoadF>
-SPX_HD void peak_stage(const PairState &ps, Best best, LoadF ldicc,
-                       double *shift2, int *peak, int *status) {
+struct PeakGeom { int idx, imax, jmax, x1, y1, mode; };   // mode 0: fit, 1: integer (NaN/edge)
+struct FitSums { double s0, su, sv, suv, suu, svv; };
+SPX_HD FitSums fit_zero() { FitSums f; f.s0 = f.su = f.sv = f.suv = f.suu = f.svv = 0.0; return f; }
+SPX_HD void fit_add(FitSums &a, const FitSums &b) {
+    a.s0 += b.s0; a.su += b.su; a.sv += b.sv; a.suv += b.suv; a.suu += b.suu; a.svv += b.svv;
+}
+
+SPX_HD PeakGeom peak_geometry(const PairState &ps) {
+    PeakGeom g;
     const int h2 = 2 * ps.ny, w2 = 2 * ps.nx;
-    int st = ps.status;
-    int idx = best.idx;
+    const int st = ps.status;
     const bool norm = ps.cc_type != SPX_CC;
     const int nf_all = SPX_S_NONFINITE_REF | SPX_S_BAD_NORM;
     const int nf_ph = SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
                       SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
-    bool nanfit = false;
+    g.idx = ps.best.idx;
+    bool nan = false;
     if ((st & nf_all) || (norm && (st & nf_ph))) {
-        idx = 0; nanfit = true;                 // whole surface NaN
-    } else if (st & nf_ph) {                    // CC: first NaN lattice, row-major
-        idx = (st & SPX_S_NONFINITE_P00) ? 0 : (st & SPX_S_NONFINITE_P10) ? 1
-            : (st & SPX_S_NONFINITE_P01) ? w2 : w2 + 1;
-        nanfit = true;
+        g.idx = 0; nan = true;                      // whole surface NaN
+    } else if (st & nf_ph) {                        // CC: first NaN lattice, row-major
+        g.idx = (st & SPX_S_NONFINITE_P00) ? 0 : (st & SPX_S_NONFINITE_P10) ? 1
+              : (st & SPX_S_NONFINITE_P01) ? w2 : w2 + 1;
+        nan = true;
     }
-    const int jmax = idx / w2, imax = idx - jmax * w2;
-    PeakOut po;
-    if (nanfit) {
-        // every 5x5 box around a NaN peak contains NaN -> find_peak returns the
-        // integer position (edge rule or NaN-coefficient fall-through)
-        po.x = double(imax); po.y = double(jmax);
-        po.status = (imax == 0 || jmax == 0) ? SPX_S_PEAK_EDGE : SPX_S_FIT_NONFINITE;
+    g.jmax = g.idx / w2; g.imax = g.idx - g.jmax * w2;
+    // centroid.py:165-184 for a 5x5 box inside a >= 6x6 image
+    g.x1 = g.imax - 2; if (g.x1 < 0) g.x1 = 0; if (g.x1 > w2 - 5) g.x1 = w2 - 5;
+    g.y1 = g.jmax - 2; if (g.y1 < 0) g.y1 = 0; if (g.y1 > h2 - 5) g.y1 = h2 - 5;
+    // every 5x5 box around a NaN peak contains NaN -> integer position; a peak in
+    // row/column 0 sits on the box edge (centroid.py:171-172) -> integer position
+    g.mode = (nan || g.imax == 0 || g.jmax == 0) ? 1 : 0;
+    if (nan) g.mode |= 2;
+    return g;
+}
+
+template <class LoadF>
+SPX_HD FitSums peak_lane(const PairState &ps, const PeakGeom &g, int lane, LoadF ldicc) {
+    FitSums f = fit_zero();
+    if (g.mode == 0 && lane < 25) {
+        const int dj = lane / 5, di = lane - 5 * dj;
+        const double d = double(ldicc((g.y1 + dj) * (2 * ps.nx) + g.x1 + di));
+        const double u = double(di - 2), v = double(dj - 2);
+        f.s0 = d; f.su = u * d; f.sv = v * d; f.suv = u * v * d; f.suu = u * u * d; f.svv = v * v * d;
+    }
+    return f;
+}
+
+SPX_HD void peak_final(const PairState &ps, const PeakGeom &g, const FitSums &f,
+                       double *shift2, int *peak, int *status) {
+    const int h2 = 2 * ps.ny, w2 = 2 * ps.nx;
+    int st = ps.status;
+    double x = double(g.imax), y = double(g.jmax);
+    if (g.mode != 0) {
+        st |= (g.imax == 0 || g.jmax == 0) ? SPX_S_PEAK_EDGE : SPX_S_FIT_NONFINITE;
     } else {
-        po = fit_peak([&](int j, int i) { return double(ldicc(j * w2 + i)); },
-                      [](int, int) { return true; }, h2, w2, imax, jmax,
-                      double(imax), double(jmax), 5, 5);
+        const double c10 = f.su / 50.0, c01 = f.sv / 50.0, c11 = f.suv / 100.0;
+        const double c20 = (f.suu - 2.0 * f.s0) / 70.0, c02 = (f.svv - 2.0 * f.s0) / 70.0;
+        const double det = 4.0 * c02 * c20 - c11 * c11;                 // centroid.py:216
+        if (det <= 0.0 || ((c20 > 0.0 && c02 >= 0.0) || (c20 >= 0.0 && c02 > 0.0))) {
+            x = double(g.x1) + 2.5; y = double(g.y1) + 2.5;             // centroid.py:217-225
+            st |= SPX_S_NO_MAXIMUM;
+        } else {
+            const double xm = (c01 * c11 - 2.0 * c02 * c10) / det + double(g.x1 + 2);
+            const double ym = (c10 * c11 - 2.0 * c01 * c20) / det + double(g.y1 + 2);
+            if (xm > 0.0 && xm < double(w2) - 1.0 && ym > 0.0 && ym < double(h2) - 1.0) {
+                x = xm; y = ym;                                          // centroid.py:230-231
+            } else {
+                st |= (xm != xm || ym != ym) ? SPX_S_FIT_NONFINITE : SPX_S_FIT_OUTSIDE;
+            }
+        }
     }
-    st |= po.status;
-    const int xc4 = (w2 - 1) / 4, yc4 = (h2 - 1) / 4;            // cc.py:89-90
-    shift2[0] = 0.5 * po.x - double(xc4);                         // cc.py:92-93
-    shift2[1] = 0.5 * po.y - double(yc4);
-    *peak = idx;
+    const int xc4 = (w2 - 1) / 4, yc4 = (h2 - 1) / 4;                   // cc.py:89-90
+    shift2[0] = 0.5 * x - double(xc4);                                   // cc.py:92-93
+    shift2[1] = 0.5 * y - double(yc4);
+    *peak = g.idx;
     *status = st;
 }
 
@@ -580,6 +624,43 @@ SPX_HD bool icc_is_nan(const PairState &ps, int status, int idx) {
     if (status & (SPX_S_NONFINITE_REF | SPX_S_BAD_NORM)) return true;
     if (norm && (status & nf_ph)) return true;
     return (status & (SPX_S_NONFINITE_P00 << lattice)) != 0;
+}
+
+// What the kernel knows about one pair before any pixel is read.
+struct PairJob {
+    const float *base[5];
+    long long pitch;
+    int H, W, x1, y1, ny, nx, cc_type, status0;
+    unsigned flags;
+    bool patch_icc;        // ICC is a user-visible output: write NaN lattices
+};
+
+// Per-pair state, filled by six threads in parallel (part 0..4: tile slots,
+// part 5: scalars).
+SPX_HD void fill_state(PairState &ps, const PairJob &job, int part) {
+    if (part < 5) {
+        ps.base[part] = job.base[part];
+        ps.pitch[part] = job.pitch;
+        ps.y0[part] = job.y1; ps.x0[part] = job.x1;
+        return;
+    }
+    ps.H = job.H; ps.W = job.W;
+    ps.ny = job.ny; ps.nx = job.nx;
+    ps.yc = (job.ny - 1) / 2; ps.xc = (job.nx - 1) / 2;
+    ps.cc_type = job.cc_type; ps.flags = job.flags;
+    ps.mu = 0.f; ps.mu_ref = 0.f; ps.rscale = 1.f;
+    ps.ylo = job.y1 < 0 ? -job.y1 : 0;
+    ps.yhi = job.y1 + job.ny > job.H ? job.H - job.y1 : job.ny;
+    ps.xlo = job.x1 < 0 ? -job.x1 : 0;
+    ps.xhi = job.x1 + job.nx > job.W ? job.W - job.x1 : job.nx;
+    ps.interior = job.x1 >= 0 && job.y1 >= 0 && job.x1 + job.nx <= job.W &&
+                  job.y1 + job.ny <= job.H;
+    ps.report = ((job.flags & SPX_F_ZERO_BAD_REF) ? 0 : SPX_S_NONFINITE_REF) |
+                ((job.flags & SPX_F_ZERO_BAD_PHASES) ? 0 :
+                 (SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 | SPX_S_NONFINITE_P01 |
+                  SPX_S_NONFINITE_P11));
+    ps.status = job.status0;
+    ps.best = best_init();
 }
 
 // --------------------------------------------------------------------------
@@ -632,8 +713,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
             });
         }
         ex.par([&](int tid) { ic1_pass<C>(c, tid); });
-        Best bb = ex.reduce_best([&](int tid) { return ic2_pass<C>(c, tid, b, ysh); });
-        ex.single([&]() { if (best_better(bb, ps->best)) ps->best = bb; });
+        ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh); });
     }
 }
 
@@ -641,48 +721,20 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 // The pass sequence for ONE pair.  `Ex` supplies the execution model:
 //   par(f)          run f(tid) for every thread of the CTA, then barrier
 //   single(f)       run f() on one thread, then barrier
-//   reduce_stats(f) / reduce_best(f): block reductions of f(tid); the result
-//                   is only meaningful inside the following single()
+//   parts(n, f)     run f(0..n-1) on n different threads, then barrier
+//   reduce_stats(f) block reduction of f(tid); meaningful in the next single()
+//   reduce_best_into(dst, f)  block argmax of f(tid) merged into *dst, barrier
+//   warp_fit(lane_f, final_f) one warp: sum lane_f(lane) over 32 lanes, then
+//                   final_f(sum) on one lane, then barrier
 //   or_status(p,v)  atomic OR
 // The device executor is in spx_cc.cu; tools/host_emu.cu runs the same
 // sequence serially on the CPU for debugging.
 // --------------------------------------------------------------------------
-struct PairJob {
-    const float *base[5];
-    long long pitch;
-    int H, W, x1, y1, ny, nx, cc_type, status0;
-    unsigned flags;
-    bool patch_icc;        // ICC is a user-visible output: write NaN lattices
-};
-
 template <class C, class Ex>
 SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
                          double *shift2, int *peak, int *status) {
     PairState *ps = c.ps;
-    ex.single([&]() {
-        for (int s = 0; s < 5; ++s) {
-            ps->base[s] = job.base[s];
-            ps->pitch[s] = job.pitch;
-            ps->y0[s] = job.y1; ps->x0[s] = job.x1;
-        }
-        ps->H = job.H; ps->W = job.W;
-        ps->ny = job.ny; ps->nx = job.nx;
-        ps->yc = (job.ny - 1) / 2; ps->xc = (job.nx - 1) / 2;
-        ps->cc_type = job.cc_type; ps->flags = job.flags;
-        ps->mu = 0.f; ps->mu_ref = 0.f; ps->rscale = 1.f;
-        ps->ylo = job.y1 < 0 ? -job.y1 : 0;
-        ps->yhi = job.y1 + job.ny > job.H ? job.H - job.y1 : job.ny;
-        ps->xlo = job.x1 < 0 ? -job.x1 : 0;
-        ps->xhi = job.x1 + job.nx > job.W ? job.W - job.x1 : job.nx;
-        ps->interior = job.x1 >= 0 && job.y1 >= 0 && job.x1 + job.nx <= job.W &&
-                       job.y1 + job.ny <= job.H;
-        ps->report = ((job.flags & SPX_F_ZERO_BAD_REF) ? 0 : SPX_S_NONFINITE_REF) |
-                     ((job.flags & SPX_F_ZERO_BAD_PHASES) ? 0 :
-                      (SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 | SPX_S_NONFINITE_P01 |
-                       SPX_S_NONFINITE_P11));
-        ps->status = job.status0;
-        ps->best = best_init();
-    });
+    ex.parts(6, [&](int part) { fill_state(*ps, job, part); });
 
     // ---- normalisation statistics (cc.py:131-156) ----------------------
     if (job.cc_type != SPX_CC) {
@@ -696,15 +748,21 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     else run_transforms<C, false>(c, ex);
 
     // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
-    ex.single([&]() {
+    {
         const float *icc = c.icc;
-        int pk, st;
-        double sh[2];
-        peak_stage(*ps, ps->best, [&](int i) { return ex.load_icc(icc + i); }, sh, &pk, &st);
-        shift2[0] = sh[0]; shift2[1] = sh[1];
-        *peak = pk; *status = st;
-        ps->status = st;
-    });
+        ex.warp_fit(
+            [&](int lane) {
+                const PeakGeom g = peak_geometry(*ps);
+                return peak_lane(*ps, g, lane, [&](int i) { return ex.load_icc(icc + i); });
+            },
+            [&](const FitSums &f) {
+                const PeakGeom g = peak_geometry(*ps);
+                int st;
+                peak_final(*ps, g, f, shift2, peak, &st);
+                *status = st;
+                ps->status = st;
+            });
+    }
     if (job.patch_icc) {
         ex.par([&](int tid) {
             const int st = ps->status;

@@ -162,8 +162,14 @@ def test_fused_frames_equals_gather_then_stack():
                 for k in range(5)]
         stack = torch.stack([c["data"].reshape(-1, 64, 64) for c in cuts], dim=1)
         sh2, pk2, st2, icc2 = batch.cc_fit_stack(stack, t, want_icc=True)
-        assert torch.equal(sh, sh2) and torch.equal(pk, pk2)
-        assert torch.equal(icc, icc2)
+        # interior boxes run the same code path in both modes: bit-identical.
+        # The 9 edge boxes take the bounds-checked path when read from the frame
+        # and the full-tile path once gathered: same maths, different rounding.
+        assert torch.equal(sh[9:], sh2[9:]) and torch.equal(pk, pk2)
+        assert torch.equal(icc[9:], icc2[9:])
+        assert float((sh[:9] - sh2[:9]).abs().max()) < 1e-5
+        rel = (icc[:9] - icc2[:9]).flatten(1).norm(dim=1) / icc2[:9].flatten(1).norm(dim=1)
+        assert float(rel.max()) < 1e-6
         host = stack.cpu().numpy()
         for k in list(range(12)) + list(range(100, 130)):
             dx, dy, oicc, _ = _oracle(host[k], t)

@@ -21,10 +21,14 @@ struct HostExec {
         for (int t = 0; t < C::T; ++t) { StatPartial s = f(t); stat_merge(tot, s); }
         return tot;
     }
-    template <class F> Best reduce_best(F f) {
-        Best g = best_init();
-        for (int t = 0; t < C::T; ++t) { Best b = f(t); if (best_better(b, g)) g = b; }
-        return g;
+    template <class F> void parts(int n, F f) { for (int t = 0; t < n; ++t) f(t); }
+    template <class F> void reduce_best_into(Best *dst, F f) {
+        for (int t = 0; t < C::T; ++t) { Best b = f(t); if (best_better(b, *dst)) *dst = b; }
+    }
+    template <class LF, class FF> void warp_fit(LF lane_f, FF final_f) {
+        FitSums tot = fit_zero();
+        for (int l = 0; l < 32; ++l) { FitSums f = lane_f(l); fit_add(tot, f); }
+        final_f(tot);
     }
     void or_status(int *p, int v) { *p |= v; }
     float load_icc(const float *p) { return *p; }

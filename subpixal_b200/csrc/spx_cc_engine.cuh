@@ -95,9 +95,6 @@ struct PairState {
     int report;            // status bits of the tiles whose NaN/Inf are reported
     int status;
     Best best;             // running argmax over the interlaced surface
-    float post_scale;      // NCC: 1/(sigma*sigma_ref), applied after the transforms
-    int need_slow;         // NCC: zeros present -> exact statistics pass needed
-    double acc[6];         // on-the-fly sums: cnt, sum, sq, (rcnt), rsum, rsq
 };
 
 template <class C>
@@ -206,9 +203,7 @@ SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
     return st;
 }
 
-// post = false: scale folded into R before the transforms (ZNCC needs the means
-// first anyway); post = true: scale applied to the finished surface (NCC).
-SPX_HD void stats_finalize(PairState &ps, const StatPartial &t, bool post = false) {
+SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
     ps.status |= t.flags;
     const bool zero = ps.cc_type == SPX_ZNCC;
     double mu = 0.0, sig = NAN, rmu = 0.0, rsig = NAN;
@@ -228,14 +223,11 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t, bool post = fals
     ps.mu_ref = zero ? float(rmu) : 0.f;
     if (!(sc == sc) || !(fabs(sc) < 1e300) || sf == 0.f || rf == 0.f) {
         ps.status |= SPX_S_BAD_NORM;
-    } else if (post) {
-        ps.post_scale = float(sc);
+        ps.rscale = 1.f;
     } else {
         ps.rscale = float(sc);
     }
-    const int nonfinite = SPX_S_NONFINITE_REF | SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
-                          SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
-    if (ps.status & nonfinite) ps.status |= SPX_S_BAD_NORM;   // NaN/Inf poisons the statistics
+    if (t.flags) ps.status |= SPX_S_BAD_NORM;   // NaN/Inf poisons the statistics
 }
 
 // --------------------------------------------------------------------------
@@ -250,7 +242,7 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t, bool post = fals
 // property of n1: reference rows exist for n1 < NMAX/E2, image rows for
 // n1 >= NMAX/(2*E2).  No bounds tests, no predicates, minimal address math.
 template <class C, bool FAST, bool IS_REF>
-SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, StatPartial *acc = nullptr) {
+SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : ps.nx, ny = FAST ? C::NMAX : ps.ny;
@@ -303,20 +295,6 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, StatParti
                 constexpr int n1 = decltype(N1)::value;
                 va[n1] = sanitize(va[n1], sa, report, flags);
                 vb[n1] = sanitize(vb[n1], pair ? sb : sa, report, flags);
-            });
-        }
-        if (acc) {      // NCC statistics on the fly (cc.py:139-142, 151-154)
-            static_for<N1_LO, N1_HI>([&](auto N1) {
-                constexpr int n1 = decltype(N1)::value;
-                const double da = double(va[n1]);
-                if (IS_REF) {
-                    acc->rsum += da; acc->rsq += da * da;
-                } else {
-                    const double db = double(vb[n1]);
-                    acc->cnt += (va[n1] != 0.f ? 1.0 : 0.0) + (vb[n1] != 0.f ? 1.0 : 0.0);
-                    acc->sum += da + db;
-                    acc->sq += da * da; acc->sq += db * db;
-                }
             });
         }
         cf x[C::E1];
@@ -596,7 +574,7 @@ SPX_HD FitSums peak_lane(const PairState &ps, const PeakGeom &g, int lane, LoadF
     FitSums f = fit_zero();
     if (g.mode == 0 && lane < 25) {
         const int dj = lane / 5, di = lane - 5 * dj;
-        const double d = double(ldicc((g.y1 + dj) * (2 * ps.nx) + g.x1 + di) * ps.post_scale);
+        const double d = double(ldicc((g.y1 + dj) * (2 * ps.nx) + g.x1 + di));
         const double u = double(di - 2), v = double(dj - 2);
         f.s0 = d; f.su = u * d; f.sv = v * d; f.suv = u * v * d; f.suu = u * u * d; f.svv = v * v * d;
     }
@@ -683,8 +661,6 @@ SPX_HD void fill_state(PairState &ps, const PairJob &job, int part) {
                   SPX_S_NONFINITE_P11));
     ps.status = job.status0;
     ps.best = best_init();
-    ps.post_scale = 1.f; ps.need_slow = 0;
-    for (int k = 0; k < 6; ++k) ps.acc[k] = 0.0;
 }
 
 // --------------------------------------------------------------------------
@@ -698,23 +674,11 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
     const int yoff = FAST ? C::NMAX / 2 : ps->yc, xoff = FAST ? C::NMAX / 2 : ps->xc;
     const int ysh = yoff - ps->yc, xsh = xoff - ps->xc;
 
-    // NCC: statistics are accumulated while the tiles stream through C1 and the
-    // scale is applied to the finished surface (no separate pass over the tiles)
-    const bool otf = ps->cc_type == SPX_NCC;
-
     // ---- reference image -> conj(R) * scale, half spectrum ---------------
-    if (otf) {
-        ex.reduce_stats_into(ps->acc, [&](int tid) {
-            StatPartial a = stat_zero();
-            a.flags = c1_pass<C, FAST, true>(c, tid, 0, -1, 0, &a);
-            return a;
-        });
-    } else {
-        ex.par([&](int tid) {
-            const int fl = c1_pass<C, FAST, true>(c, tid, 0, -1, 0);
-            if (fl) ex.or_status(&ps->status, fl);
-        });
-    }
+    ex.par([&](int tid) {
+        const int fl = c1_pass<C, FAST, true>(c, tid, 0, -1, 0);
+        if (fl) ex.or_status(&ps->status, fl);
+    });
     ex.par([&](int tid) { c2_pass<C>(c, tid); });
     for (int b0 = 0; b0 < C::RH; b0 += 32) {
         ex.par([&](int tid) {
@@ -729,18 +693,10 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
-        if (otf) {
-            ex.reduce_stats_into(ps->acc, [&](int tid) {
-                StatPartial a = stat_zero();
-                a.flags = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, &a);
-                return a;
-            });
-        } else {
-            ex.par([&](int tid) {
-                const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff);
-                if (fl) ex.or_status(&ps->status, fl);
-            });
-        }
+        ex.par([&](int tid) {
+            const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff);
+            if (fl) ex.or_status(&ps->status, fl);
+        });
         ex.par([&](int tid) { c2_pass<C>(c, tid); });
         for (int b0 = 0; b0 < C::P; b0 += 32) {
             ex.par([&](int tid) {
@@ -759,26 +715,6 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
         ex.par([&](int tid) { ic1_pass<C>(c, tid); });
         ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh); });
     }
-
-    if (otf) {
-        // every pixel of the four phases non-zero (the usual case): the union mask
-        // of cc.py:150 is the whole cutout and the sums above are the statistics.
-        // Otherwise (masked / zero-filled pixels) redo them exactly, mask-aware.
-        ex.single([&]() {
-            const double npix = double(ps->ny) * double(ps->nx);
-            ps->need_slow = ps->acc[0] != 4.0 * npix;
-            if (!ps->need_slow) {
-                StatPartial t = stat_zero();
-                t.cnt = ps->acc[0]; t.sum = ps->acc[1]; t.sq = ps->acc[2];
-                t.rcnt = npix; t.rsum = ps->acc[4]; t.rsq = ps->acc[5];
-                stats_finalize(*ps, t, true);
-            }
-        });
-        if (ps->need_slow) {
-            StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(*ps, tid); });
-            ex.single([&]() { stats_finalize(*ps, tot, true); });
-        }
-    }
 }
 
 // --------------------------------------------------------------------------
@@ -787,7 +723,6 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 //   single(f)       run f() on one thread, then barrier
 //   parts(n, f)     run f(0..n-1) on n different threads, then barrier
 //   reduce_stats(f) block reduction of f(tid); meaningful in the next single()
-//   reduce_stats_into(acc6, f)  same, added to acc6[0..5] (+ flags into status), barrier
 //   reduce_best_into(dst, f)  block argmax of f(tid) merged into *dst, barrier
 //   warp_fit(lane_f, final_f) one warp: sum lane_f(lane) over 32 lanes, then
 //                   final_f(sum) on one lane, then barrier
@@ -802,7 +737,7 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     ex.parts(6, [&](int part) { fill_state(*ps, job, part); });
 
     // ---- normalisation statistics (cc.py:131-156) ----------------------
-    if (job.cc_type == SPX_ZNCC) {     // the means are needed before the transforms
+    if (job.cc_type != SPX_CC) {
         StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(*ps, tid); });
         ex.single([&]() { stats_finalize(*ps, tot); });
     }
@@ -833,15 +768,11 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
             const int st = ps->status;
             const int nanbits = SPX_S_NONFINITE_REF | SPX_S_BAD_NORM | SPX_S_NONFINITE_P00 |
                                 SPX_S_NONFINITE_P10 | SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
-            const int ne = 4 * ps->ny * ps->nx;
-            const float sc = ps->post_scale;
-            if (sc != 1.f && !(st & nanbits)) {
-                for (int i = tid; i < ne; i += C::T) c.icc[i] *= sc;
-            }
             if (st & nanbits) {
+                const int ne = 4 * ps->ny * ps->nx;
                 union { unsigned u; float f; } qnan; qnan.u = 0x7fc00000u;
                 for (int i = tid; i < ne; i += C::T)
-                    c.icc[i] = icc_is_nan(*ps, st, i) ? qnan.f : c.icc[i] * sc;
+                    if (icc_is_nan(*ps, st, i)) c.icc[i] = qnan.f;
             }
         });
     }

@@ -174,32 +174,45 @@ template <class C>
 SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
     StatPartial st = stat_zero();
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = ps.nx, report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
-    for (int x = lane; x < nx; x += 32) {
-        TileCol tc[5];
-#pragma unroll
-        for (int s = 0; s < 5; ++s) tc[s] = tile_col(ps, s, x, true);
-        // rows outside [ylo, yhi) are fill pixels: zero in every tile, so they
-        // contribute to no sum (cc.py:134-137 masks zeros)
+    const int report = ps.report, ylo = ps.ylo, yhi = ps.yhi, xlo = ps.xlo, xhi = ps.xhi;
+    const int pitch = int(ps.pitch[0]);
+    const long long step = (long long)C::NW * pitch;
+    int cnt = 0, rcnt = 0;
+    // Pixels outside [ylo,yhi) x [xlo,xhi) are fill pixels: zero in every tile, so
+    // they take part in no sum (cc.py:134-137 masks zeros).  The five tiles share
+    // the box geometry, so one element offset serves all five base pointers.
+    for (int x = xlo + lane; x < xhi; x += 32) {
+        const long long off = (long long)(ps.y0[0] + ylo + warp) * pitch + (x + ps.x0[0]);
+        const float *p0 = ps.base[0] + off, *p1 = ps.base[1] + off, *p2 = ps.base[2] + off,
+                    *p3 = ps.base[3] + off, *p4 = ps.base[4] + off;
         for (int y = ylo + warp; y < yhi; y += C::NW) {
             float v[5];
+            v[0] = ld_f32(p0); v[1] = ld_f32(p1); v[2] = ld_f32(p2);
+            v[3] = ld_f32(p3); v[4] = ld_f32(p4);
+            p0 += step; p1 += step; p2 += step; p3 += step; p4 += step;
+            unsigned worst = 0u;
 #pragma unroll
-            for (int s = 0; s < 5; ++s)
-                v[s] = tc[s].colok ? ld_f32(tc[s].p + y * tc[s].pitch) : 0.f;
+            for (int s = 0; s < 5; ++s) {
+                const unsigned u = f32_bits(v[s]) & 0x7fffffffu;
+                worst = worst > u ? worst : u;
+            }
+            if (worst >= 0x7f800000u) {                      // rare: NaN / Inf present
+#pragma unroll
+                for (int s = 0; s < 5; ++s) v[s] = sanitize(v[s], s, report, st.flags);
+            }
             bool any = false;
 #pragma unroll
             for (int s = 1; s < 5; ++s) {
-                const float q = sanitize(v[s], s, report, st.flags);
-                const bool nz = q != 0.f;                     // cc.py:134-137
-                const double d = double(q);
-                st.cnt += nz ? 1.0 : 0.0; st.sum += d; st.sq += d * d;
+                const bool nz = v[s] != 0.f;                  // cc.py:134-137
+                const double d = double(v[s]);
+                cnt += nz ? 1 : 0; st.sum += d; st.sq += d * d;
                 any |= nz;
             }
-            const float r = sanitize(v[0], 0, report, st.flags);
-            const double d = any ? double(r) : 0.0;           // cc.py:150-154
-            st.rcnt += any ? 1.0 : 0.0; st.rsum += d; st.rsq += d * d;
+            const double d = double(any ? v[0] : 0.f);        // cc.py:150-154
+            rcnt += any ? 1 : 0; st.rsum += d; st.rsq += d * d;
         }
     }
+    st.cnt = double(cnt); st.rcnt = double(rcnt);
     return st;
 }
 

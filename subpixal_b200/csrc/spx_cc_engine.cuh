@@ -123,6 +123,15 @@ SPX_HD float ld_f32(const float *p) {
     return *p;
 #endif
 }
+// last use of a tile pixel: streaming load (evict-first), so the input stream
+// does not push the L2-resident per-CTA scratch out to HBM
+SPX_HD float ld_f32_last(const float *p) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
 
 // W row r holds frequency ky = r/E2 + E1*(r%E2)  (in-place two-step order)
 template <class C> SPX_HD int ky_of_row(int r) { return r / C::E2 + C::E1 * (r % C::E2); }
@@ -181,35 +190,49 @@ SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
     // Pixels outside [ylo,yhi) x [xlo,xhi) are fill pixels: zero in every tile, so
     // they take part in no sum (cc.py:134-137 masks zeros).  The five tiles share
     // the box geometry, so one element offset serves all five base pointers.
+    constexpr int U = 4;                                     // rows in flight per lane
     for (int x = xlo + lane; x < xhi; x += 32) {
         const long long off = (long long)(ps.y0[0] + ylo + warp) * pitch + (x + ps.x0[0]);
-        const float *p0 = ps.base[0] + off, *p1 = ps.base[1] + off, *p2 = ps.base[2] + off,
-                    *p3 = ps.base[3] + off, *p4 = ps.base[4] + off;
-        for (int y = ylo + warp; y < yhi; y += C::NW) {
-            float v[5];
-            v[0] = ld_f32(p0); v[1] = ld_f32(p1); v[2] = ld_f32(p2);
-            v[3] = ld_f32(p3); v[4] = ld_f32(p4);
-            p0 += step; p1 += step; p2 += step; p3 += step; p4 += step;
+        const float *p[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) p[s] = ps.base[s] + off;
+        for (int y = ylo + warp; y < yhi; y += U * C::NW) {
+            float v[U][5];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                    // all loads first
+                const bool ok = y + u * C::NW < yhi;
+#pragma unroll
+                for (int s = 0; s < 5; ++s) v[u][s] = ok ? ld_f32(p[s] + u * step) : 0.f;
+            }
+#pragma unroll
+            for (int s = 0; s < 5; ++s) p[s] += U * step;
             unsigned worst = 0u;
 #pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                const unsigned u = f32_bits(v[s]) & 0x7fffffffu;
-                worst = worst > u ? worst : u;
-            }
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int s = 0; s < 5; ++s) {
+                    const unsigned b = f32_bits(v[u][s]) & 0x7fffffffu;
+                    worst = worst > b ? worst : b;
+                }
             if (worst >= 0x7f800000u) {                      // rare: NaN / Inf present
 #pragma unroll
-                for (int s = 0; s < 5; ++s) v[s] = sanitize(v[s], s, report, st.flags);
-            }
-            bool any = false;
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int s = 1; s < 5; ++s) {
-                const bool nz = v[s] != 0.f;                  // cc.py:134-137
-                const double d = double(v[s]);
-                cnt += nz ? 1 : 0; st.sum += d; st.sq += d * d;
-                any |= nz;
+                    for (int s = 0; s < 5; ++s) v[u][s] = sanitize(v[u][s], s, report, st.flags);
             }
-            const double d = double(any ? v[0] : 0.f);        // cc.py:150-154
-            rcnt += any ? 1 : 0; st.rsum += d; st.rsq += d * d;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bool any = false;
+#pragma unroll
+                for (int s = 1; s < 5; ++s) {
+                    const bool nz = v[u][s] != 0.f;           // cc.py:134-137
+                    const double d = double(v[u][s]);
+                    cnt += nz ? 1 : 0; st.sum += d; st.sq += d * d;
+                    any |= nz;
+                }
+                const double d = double(any ? v[u][0] : 0.f); // cc.py:150-154
+                rcnt += any ? 1 : 0; st.rsum += d; st.rsq += d * d;
+            }
         }
     }
     st.cnt = double(cnt); st.rcnt = double(rcnt);
@@ -283,16 +306,16 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
             constexpr int n1 = decltype(N1)::value;
             if constexpr (FAST) {
                 if constexpr (n1 >= N1_LO && n1 < N1_HI) {
-                    va[n1] = ld_f32(pa0 + n1 * rs);
-                    vb[n1] = pair ? ld_f32(pb0 + n1 * rs) : 0.f;
+                    va[n1] = ld_f32_last(pa0 + n1 * rs);
+                    vb[n1] = pair ? ld_f32_last(pb0 + n1 * rs) : 0.f;
                 } else {
                     va[n1] = 0.f; vb[n1] = 0.f;
                 }
             } else {
                 const int y = C::E2 * n1 + ybase;
                 const bool ok = y >= ylo && y < yhi;         // warp-uniform
-                va[n1] = (ok && ta.colok) ? ld_f32(pa0 + n1 * rs) : 0.f;
-                vb[n1] = (ok && tb.colok) ? ld_f32(pb0 + n1 * rs) : 0.f;
+                va[n1] = (ok && ta.colok) ? ld_f32_last(pa0 + n1 * rs) : 0.f;
+                vb[n1] = (ok && tb.colok) ? ld_f32_last(pb0 + n1 * rs) : 0.f;
             }
         });
         // one cheap test for "any NaN/Inf among my pixels": max of |bits|

@@ -27,9 +27,9 @@ struct CcParams {
 };
 
 // ---- configurations (one per supported maximum cutout size) -----------------
-//                P   E1  E2 NMAX   T  MINB  W_SMEM R_SMEM
-using Cfg32  = CcCfg< 48,  6,  8,  32, 128, 4, true,  true >;
-using Cfg64  = CcCfg< 96, 12,  8,  64, 256, 2, true,  true >;
+//                P   E1  E2 NMAX   T  MINB  W_SMEM R_SMEM INPLACE
+using Cfg32  = CcCfg< 48,  6,  8,  32, 128, 4, true,  true,  true>;
+using Cfg64  = CcCfg< 96, 12,  8,  64, 256, 2, true,  true,  true>;
 using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
 using Cfg256 = CcCfg<384, 24, 16, 256, 256, 1, false, false>;
 

@@ -59,18 +59,24 @@ SPX_TW(48) SPX_TW(96) SPX_TW(192) SPX_TW(384)
 // --------------------------------------------------------------------------
 // configuration
 // --------------------------------------------------------------------------
-template <int P_, int E1_, int E2_, int NMAX_, int T_, int MINB_, bool WSM_, bool RSM_>
+// INPLACE: W is P x (P+1) and the row stage (X1, X2, X3) works in place on whole
+// rows - three barriers per row stage and no separate scratch.  Otherwise W is
+// P x (NMAX+1) and the row stage goes through a 32-row scratch S, batch by batch
+// (used when W lives in global memory).
+template <int P_, int E1_, int E2_, int NMAX_, int T_, int MINB_, bool WSM_, bool RSM_,
+          bool INPLACE_ = false>
 struct CcCfg {
     static constexpr int P = P_, E1 = E1_, E2 = E2_, NMAX = NMAX_, T = T_, MINB = MINB_;
-    static constexpr bool W_SMEM = WSM_, R_SMEM = RSM_;
+    static constexpr bool W_SMEM = WSM_, R_SMEM = RSM_, INPLACE = INPLACE_;
     static constexpr int NW = T / 32;
-    static constexpr int WP = NMAX + 1;      // pitch of W (complex), odd
+    static constexpr int WP = INPLACE ? P + 1 : NMAX + 1;   // pitch of W (complex), odd
     static constexpr int SP = P + 1;         // pitch of the row scratch, odd
     static constexpr int RP = P + 1;         // pitch of R, odd
     static constexpr int RH = P / 2 + 1;     // rows of R (half spectrum)
     static constexpr int BATCH = 32;         // rows per row-op batch (= lanes)
+    static constexpr int NCHUNK = (P + 31) / 32, RCHUNK = (RH + 31) / 32;
     static constexpr size_t W_ELEMS = size_t(P) * WP;
-    static constexpr size_t S_ELEMS = size_t(BATCH) * SP;
+    static constexpr size_t S_ELEMS = INPLACE ? 0 : size_t(BATCH) * SP;
     static constexpr size_t R_ELEMS = size_t(RH) * RP;
     static_assert(E1 * E2 == P, "P = E1*E2");
     static_assert(P % 2 == 0 && NMAX % 2 == 0, "even sizes");
@@ -278,7 +284,7 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
 // property of n1: reference rows exist for n1 < NMAX/E2, image rows for
 // n1 >= NMAX/(2*E2).  No bounds tests, no predicates, minimal address math.
 template <class C, bool FAST, bool IS_REF>
-SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
+SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : ps.nx, ny = FAST ? C::NMAX : ps.ny;
@@ -356,7 +362,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
         if (active) {
             static_for<0, C::E1>([&](auto K1) {
                 constexpr int k1 = decltype(K1)::value;
-                c.W[(k1 * C::E2 + n2) * C::WP + i] = cmul(x[k1], tw<C::P>(n2 * k1));
+                c.W[(k1 * C::E2 + n2) * C::WP + i + col0] = cmul(x[k1], tw<C::P>(n2 * k1));
             });
         }
     }
@@ -365,7 +371,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff) {
 
 // C2: E2-point FFT over n2 for every (column, k1), in place.
 template <class C>
-SPX_HD void c2_pass(const Ctx<C> &c, int tid) {
+SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
@@ -375,19 +381,19 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid) {
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            x[n2] = c.W[(k1 * C::E2 + n2) * C::WP + i];
+            x[n2] = c.W[(k1 * C::E2 + n2) * C::WP + i + col0];
         });
         RegFFT<C::E2, false>::run(x);
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            c.W[(k1 * C::E2 + k2) * C::WP + i] = x[k2];
+            c.W[(k1 * C::E2 + k2) * C::WP + i + col0] = x[k2];
         });
     }
 }
 
 // IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
 template <class C>
-SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
+SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
@@ -397,12 +403,12 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
         cf x[C::E2];
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            x[k2] = c.W[(k1 * C::E2 + k2) * C::WP + l];
+            x[k2] = c.W[(k1 * C::E2 + k2) * C::WP + l + col0];
         });
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            c.W[(k1 * C::E2 + n2) * C::WP + l] = cmulc(x[n2], tw<C::P>(n2 * k1));
+            c.W[(k1 * C::E2 + n2) * C::WP + l + col0] = cmulc(x[n2], tw<C::P>(n2 * k1));
         });
     }
 }
@@ -412,7 +418,7 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid) {
 // Inputs were sanitised, so the surface is finite and a plain ">" scan in
 // increasing index order implements numpy's first-maximum rule per item.
 template <class C>
-SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift) {
+SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int ny = ps.ny, nx = ps.nx;
@@ -426,7 +432,7 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift) {
         cf x[C::E1];
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
-            x[k1] = c.W[(k1 * C::E2 + n2) * C::WP + l];
+            x[k1] = c.W[(k1 * C::E2 + n2) * C::WP + l + col0];
         });
         RegFFT<C::E1, true>::run(x);
         // sample n = E2*n1 + n2 is lag (n - shift) - yc -> surface row 2*(n-shift)+b
@@ -451,56 +457,81 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift) {
 }
 
 // --------------------------------------------------------------------------
-// row passes on one batch of 32 rows; lane <-> row
+// row passes; lane <-> row.  A warp-item is (chunk of 32 rows, n2 or k1); the
+// passes loop over the chunks [cb, ce).  INPLACE: the row's P samples live in
+// W itself (column = padded position), all chunks in one go.  Otherwise the
+// exchange goes through the scratch S and the caller runs one chunk at a time.
 // --------------------------------------------------------------------------
-// X1: r = W row handled by this lane (or -1), xoff = column offset of the tile
+template <class C, bool IS_REF>
+SPX_HD int row_of(const Ctx<C> &c, int chunk, int lane) {
+    const int k = chunk * 32 + lane;
+    if (IS_REF) return k < C::RH ? int(c.rrow[k]) : -1;
+    return k < C::P ? k : -1;
+}
+template <class C>
+SPX_HD cf *srow_of(const Ctx<C> &c, int r, int lane) {
+    return C::INPLACE ? c.W + (r >= 0 ? r : 0) * C::WP : c.S + lane * C::SP;
+}
+
+// X1: E1-point FFT along x of the nx input samples (padded position m = E2*n1+n2,
+// input column m - xoff)
 template <class C, bool FAST, bool IS_REF>
-SPX_HD void x1_pass(const Ctx<C> &c, int tid, int r, int xoff) {
+SPX_HD void x1_pass(const Ctx<C> &c, int tid, int cb, int ce, int xoff) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : c.ps->nx;
-    const cf *Wrow = c.W + (r >= 0 ? r : 0) * C::WP - xoff;
     constexpr int N1_LO = (FAST && !IS_REF) ? C::NMAX / (2 * C::E2) : 0;
     constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
-    for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
+    for (int wi = cb * C::E2 + warp; wi < ce * C::E2; wi += C::NW) {
+        const int chunk = wi / C::E2, n2 = wi - chunk * C::E2;
+        const int r = row_of<C, IS_REF>(c, chunk, lane);
+        if (C::INPLACE && r < 0) continue;
+        // INPLACE: columns are padded positions; otherwise W holds input columns
+        const cf *in = c.W + (r >= 0 ? r : 0) * C::WP - (C::INPLACE ? 0 : xoff);
+        cf *srow = srow_of<C>(c, r, lane);
         cf x[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             if constexpr (FAST) {
                 if constexpr (n1 >= N1_LO && n1 < N1_HI)
-                    x[n1] = (IS_REF && r < 0) ? cmake(0.f, 0.f) : Wrow[C::E2 * n1 + n2];
+                    x[n1] = (r < 0) ? cmake(0.f, 0.f) : in[C::E2 * n1 + n2];
                 else
                     x[n1] = cmake(0.f, 0.f);
             } else {
                 const int i = C::E2 * n1 + n2 - xoff;
-                x[n1] = (r >= 0 && i >= 0 && i < nx) ? Wrow[C::E2 * n1 + n2] : cmake(0.f, 0.f);
+                x[n1] = (r >= 0 && i >= 0 && i < nx) ? in[C::E2 * n1 + n2] : cmake(0.f, 0.f);
             }
         });
         RegFFT<C::E1, false>::run(x);
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
-            c.S[lane * C::SP + k1 * C::E2 + n2] = cmul(x[k1], tw<C::P>(n2 * k1));
+            srow[k1 * C::E2 + n2] = cmul(x[k1], tw<C::P>(n2 * k1));
         });
     }
 }
 
 // X2 for the reference image: finish the forward transform and store
-// conj(R) * rscale for ky <= P/2.
+// conj(R) * scale for ky <= P/2.
 template <class C>
-SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int ky) {
+SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int cb, int ce) {
     const int warp = warp_of(tid), lane = tid & 31;
     // normalisation scale and the 1/P^2 of the unnormalised inverse FFTs
     const float sc = c.ps->rscale * (1.0f / (float(C::P) * float(C::P)));
-    for (int k1 = warp; k1 < C::E1; k1 += C::NW) {
+    for (int wi = cb * C::E1 + warp; wi < ce * C::E1; wi += C::NW) {
+        const int chunk = wi / C::E1, k1 = wi - chunk * C::E1;
+        const int r = row_of<C, true>(c, chunk, lane);
+        if (C::INPLACE && r < 0) continue;
+        const cf *srow = srow_of<C>(c, r, lane);
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            x[n2] = c.S[lane * C::SP + k1 * C::E2 + n2];
+            x[n2] = srow[k1 * C::E2 + n2];
         });
         RegFFT<C::E2, false>::run(x);
-        if (ky >= 0) {
+        if (r >= 0) {
+            cf *Rrow = c.R + ky_of_row<C>(r) * C::RP + k1 * C::E2;
             static_for<0, C::E2>([&](auto K2) {
                 constexpr int k2 = decltype(K2)::value;
-                c.R[ky * C::RP + k1 * C::E2 + k2] = cmake(x[k2].x * sc, -x[k2].y * sc);
+                Rrow[k2] = cmake(x[k2].x * sc, -x[k2].y * sc);
             });
         }
     }
@@ -508,16 +539,20 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int ky) {
 
 // X2: forward E2-FFT, multiply by conj(R[ky, kx]), inverse E2-FFT (+twiddle)
 template <class C>
-SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
+SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int ky = r >= 0 ? ky_of_row<C>(r) : 0;
-    const bool flip = ky > C::P / 2;
-    const cf *Rrow = c.R + (flip ? C::P - ky : ky) * C::RP;
-    for (int k1 = warp; k1 < C::E1; k1 += C::NW) {
+    for (int wi = cb * C::E1 + warp; wi < ce * C::E1; wi += C::NW) {
+        const int chunk = wi / C::E1, k1 = wi - chunk * C::E1;
+        const int r = row_of<C, false>(c, chunk, lane);
+        if (C::INPLACE && r < 0) continue;
+        cf *srow = srow_of<C>(c, r, lane);
+        const int ky = r >= 0 ? ky_of_row<C>(r) : 0;
+        const bool flip = ky > C::P / 2;
+        const cf *Rrow = c.R + (flip ? C::P - ky : ky) * C::RP;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            x[n2] = c.S[lane * C::SP + k1 * C::E2 + n2];
+            x[n2] = srow[k1 * C::E2 + n2];
         });
         RegFFT<C::E2, false>::run(x);
         // column of kx = k1 + E1*k2 is k1*E2 + k2; the mirrored frequency
@@ -535,28 +570,35 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int r) {
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            c.S[lane * C::SP + k1 * C::E2 + n2] = cmulc(x[n2], tw<C::P>(n2 * k1));
+            srow[k1 * C::E2 + n2] = cmulc(x[n2], tw<C::P>(n2 * k1));
         });
     }
 }
 
-// X3: E1-point inverse FFT over k1, keep samples m = E2*n1+n2 < nx
+// X3: E1-point inverse FFT over k1; sample m = E2*n1+n2 is lag (m - shift) - xc,
+// kept for 0 <= m - shift < nx.  INPLACE keeps it at column m, otherwise it goes
+// to column m - shift of W.
 template <class C>
-SPX_HD void x3_pass(const Ctx<C> &c, int tid, int r, int shift) {
+SPX_HD void x3_pass(const Ctx<C> &c, int tid, int cb, int ce, int shift) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
-    for (int n2 = warp; n2 < C::E2; n2 += C::NW) {
+    for (int wi = cb * C::E2 + warp; wi < ce * C::E2; wi += C::NW) {
+        const int chunk = wi / C::E2, n2 = wi - chunk * C::E2;
+        const int r = row_of<C, false>(c, chunk, lane);
+        if (C::INPLACE && r < 0) continue;
+        const cf *srow = srow_of<C>(c, r, lane);
         cf x[C::E1];
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
-            x[k1] = c.S[lane * C::SP + k1 * C::E2 + n2];
+            x[k1] = srow[k1 * C::E2 + n2];
         });
         RegFFT<C::E1, true>::run(x);
         if (r >= 0) {
+            cf *out = c.W + r * C::WP - (C::INPLACE ? 0 : shift);
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
-                const int m = C::E2 * n1 + n2 - shift;      // lag m - xc
-                if (unsigned(m) < unsigned(nx)) c.W[r * C::WP + m] = x[n1];
+                const int m = C::E2 * n1 + n2;
+                if (unsigned(m - shift) < unsigned(nx)) out[m] = x[n1];
             });
         }
     }
@@ -709,47 +751,46 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
     // wanted lags: sample m of the circular correlation is lag (m - off)
     const int yoff = FAST ? C::NMAX / 2 : ps->yc, xoff = FAST ? C::NMAX / 2 : ps->xc;
     const int ysh = yoff - ps->yc, xsh = xoff - ps->xc;
+    // INPLACE: W columns are padded positions (input column i sits at i + xoff,
+    // wanted lag sample l at l + xsh)
+    const int cin = C::INPLACE ? xoff : 0, cout = C::INPLACE ? xsh : 0;
 
     // ---- reference image -> conj(R) * scale, half spectrum ---------------
     ex.par([&](int tid) {
-        const int fl = c1_pass<C, FAST, true>(c, tid, 0, -1, 0);
+        const int fl = c1_pass<C, FAST, true>(c, tid, 0, -1, 0, 0);
         if (fl) ex.or_status(&ps->status, fl);
     });
-    ex.par([&](int tid) { c2_pass<C>(c, tid); });
-    for (int b0 = 0; b0 < C::RH; b0 += 32) {
-        ex.par([&](int tid) {
-            const int k = b0 + (tid & 31);
-            x1_pass<C, FAST, true>(c, tid, k < C::RH ? int(c.rrow[k]) : -1, 0);
-        });
-        ex.par([&](int tid) {
-            const int k = b0 + (tid & 31);
-            x2_ref_pass<C>(c, tid, k < C::RH ? ky_of_row<C>(int(c.rrow[k])) : -1);
-        });
+    ex.par([&](int tid) { c2_pass<C>(c, tid, 0); });
+    if (C::INPLACE) {
+        ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, 0, C::RCHUNK, 0); });
+        ex.par([&](int tid) { x2_ref_pass<C>(c, tid, 0, C::RCHUNK); });
+    } else {
+        for (int b = 0; b < C::RCHUNK; ++b) {
+            ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, b, b + 1, 0); });
+            ex.par([&](int tid) { x2_ref_pass<C>(c, tid, b, b + 1); });
+        }
     }
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
         ex.par([&](int tid) {
-            const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff);
+            const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin);
             if (fl) ex.or_status(&ps->status, fl);
         });
-        ex.par([&](int tid) { c2_pass<C>(c, tid); });
-        for (int b0 = 0; b0 < C::P; b0 += 32) {
-            ex.par([&](int tid) {
-                const int r = b0 + (tid & 31);
-                x1_pass<C, FAST, false>(c, tid, r < C::P ? r : -1, xoff);
-            });
-            ex.par([&](int tid) {
-                const int r = b0 + (tid & 31);
-                x2_pass<C>(c, tid, r < C::P ? r : -1);
-            });
-            ex.par([&](int tid) {
-                const int r = b0 + (tid & 31);
-                x3_pass<C>(c, tid, r < C::P ? r : -1, xsh);
-            });
+        ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
+        if (C::INPLACE) {
+            ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
+            ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
+            ex.par([&](int tid) { x3_pass<C>(c, tid, 0, C::NCHUNK, xsh); });
+        } else {
+            for (int k = 0; k < C::NCHUNK; ++k) {
+                ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff); });
+                ex.par([&](int tid) { x2_pass<C>(c, tid, k, k + 1); });
+                ex.par([&](int tid) { x3_pass<C>(c, tid, k, k + 1, xsh); });
+            }
         }
-        ex.par([&](int tid) { ic1_pass<C>(c, tid); });
-        ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh); });
+        ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });
+        ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh, cout); });
     }
 }
 

@@ -14,7 +14,14 @@ using namespace spx;
 
 template <class C>
 struct HostExec {
-    template <class F> void par(F f) { for (int t = 0; t < C::T; ++t) f(t); }
+    // SPX_EMU_ORDER=1: reversed, =2: warps interleaved - a pass whose result depends on
+    // the thread order has an intra-pass data hazard
+    template <class F> void par(F f) {
+        static const int order = getenv("SPX_EMU_ORDER") ? atoi(getenv("SPX_EMU_ORDER")) : 0;
+        if (order == 1) { for (int t = C::T - 1; t >= 0; --t) f(t); }
+        else if (order == 2) { for (int l = 0; l < 32; ++l) for (int w = C::NW - 1; w >= 0; --w) f(w * 32 + l); }
+        else { for (int t = 0; t < C::T; ++t) f(t); }
+    }
     template <class F> void single(F f) { f(); }
     template <class F> StatPartial reduce_stats(F f) {
         StatPartial tot = stat_zero();
@@ -37,7 +44,7 @@ struct HostExec {
 template <class C>
 void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts, int *peak,
          int *status, float *icc) {
-    std::vector<cf> W(C::W_ELEMS), S(C::S_ELEMS), R(C::R_ELEMS);
+    std::vector<cf> W(C::W_ELEMS), S(C::S_ELEMS + 1), R(C::R_ELEMS);
     std::vector<uint16_t> rrow(C::RH);
     build_rrow<C>(rrow.data());
     PairState ps;
@@ -69,8 +76,8 @@ int main(int argc, char **argv) {
     std::vector<int> peak(n), status(n);
     std::vector<float> icc(size_t(n) * 4 * ny * nx);
     const int m = ny > nx ? ny : nx;
-    if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
-    else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, false, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else run<CcCfg<384, 24, 16, 256, 256, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     f = fopen(argv[2], "wb");

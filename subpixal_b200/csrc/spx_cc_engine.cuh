@@ -473,6 +473,34 @@ SPX_HD cf *srow_of(const Ctx<C> &c, int r, int lane) {
     return C::INPLACE ? c.W + (r >= 0 ? r : 0) * C::WP : c.S + lane * C::SP;
 }
 
+// Staged mode (W in global memory): coalesced copy of one batch of rows between
+// W (columns = input / lag index) and the scratch S (columns = padded position);
+// one warp per row, lanes along the row.
+template <class C, bool IS_REF>
+SPX_HD void stage_in(const Ctx<C> &c, int tid, int chunk, int xoff) {
+    const int warp = warp_of(tid), lane = tid & 31;
+    const int nx = c.ps->nx;
+    for (int k = warp; k < 32; k += C::NW) {
+        const int r = row_of<C, IS_REF>(c, chunk, k);
+        if (r < 0) continue;
+        const cf *src = c.W + r * C::WP;
+        cf *dst = c.S + k * C::SP + xoff;
+        for (int i = lane; i < nx; i += 32) dst[i] = src[i];
+    }
+}
+template <class C>
+SPX_HD void stage_out(const Ctx<C> &c, int tid, int chunk, int shift) {
+    const int warp = warp_of(tid), lane = tid & 31;
+    const int nx = c.ps->nx;
+    for (int k = warp; k < 32; k += C::NW) {
+        const int r = row_of<C, false>(c, chunk, k);
+        if (r < 0) continue;
+        const cf *src = c.S + k * C::SP + shift;
+        cf *dst = c.W + r * C::WP;
+        for (int l = lane; l < nx; l += 32) dst[l] = src[l];
+    }
+}
+
 // X1: E1-point FFT along x of the nx input samples (padded position m = E2*n1+n2,
 // input column m - xoff)
 template <class C, bool FAST, bool IS_REF>
@@ -485,9 +513,10 @@ SPX_HD void x1_pass(const Ctx<C> &c, int tid, int cb, int ce, int xoff) {
         const int chunk = wi / C::E2, n2 = wi - chunk * C::E2;
         const int r = row_of<C, IS_REF>(c, chunk, lane);
         if (C::INPLACE && r < 0) continue;
-        // INPLACE: columns are padded positions; otherwise W holds input columns
-        const cf *in = c.W + (r >= 0 ? r : 0) * C::WP - (C::INPLACE ? 0 : xoff);
+        // the row buffer (W row itself, or the staged copy in S) is indexed by
+        // padded position
         cf *srow = srow_of<C>(c, r, lane);
+        const cf *in = srow;
         cf x[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
@@ -576,8 +605,7 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
 }
 
 // X3: E1-point inverse FFT over k1; sample m = E2*n1+n2 is lag (m - shift) - xc,
-// kept for 0 <= m - shift < nx.  INPLACE keeps it at column m, otherwise it goes
-// to column m - shift of W.
+// kept (at position m of the row buffer) for 0 <= m - shift < nx.
 template <class C>
 SPX_HD void x3_pass(const Ctx<C> &c, int tid, int cb, int ce, int shift) {
     const int warp = warp_of(tid), lane = tid & 31;
@@ -594,7 +622,7 @@ SPX_HD void x3_pass(const Ctx<C> &c, int tid, int cb, int ce, int shift) {
         });
         RegFFT<C::E1, true>::run(x);
         if (r >= 0) {
-            cf *out = c.W + r * C::WP - (C::INPLACE ? 0 : shift);
+            cf *out = srow_of<C>(c, r, lane);
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
                 const int m = C::E2 * n1 + n2;
@@ -766,6 +794,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
         ex.par([&](int tid) { x2_ref_pass<C>(c, tid, 0, C::RCHUNK); });
     } else {
         for (int b = 0; b < C::RCHUNK; ++b) {
+            ex.par([&](int tid) { stage_in<C, true>(c, tid, b, 0); });
             ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, b, b + 1, 0); });
             ex.par([&](int tid) { x2_ref_pass<C>(c, tid, b, b + 1); });
         }
@@ -784,9 +813,11 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
             ex.par([&](int tid) { x3_pass<C>(c, tid, 0, C::NCHUNK, xsh); });
         } else {
             for (int k = 0; k < C::NCHUNK; ++k) {
+                ex.par([&](int tid) { stage_in<C, false>(c, tid, k, xoff); });
                 ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff); });
                 ex.par([&](int tid) { x2_pass<C>(c, tid, k, k + 1); });
                 ex.par([&](int tid) { x3_pass<C>(c, tid, k, k + 1, xsh); });
+                ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
             }
         }
         ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });

@@ -178,6 +178,18 @@ int spx_find_peak(const void *surfaces, int kind, int n, int h, int w,
                   int search_wx, int search_wy, int fit_wx, int fit_wy,
                   double *xy, int32_t *peak, int32_t *status, void *stream);
 
+/* ========================================================================
+ * (5) Bounding boxes of all labels of a segmentation image in one pass.
+ * Replaces the per-source full-frame scan of create_primary_cutouts
+ * (cutout.py:151-162: `seg == sid`, np.where, min / max for every source).
+ * seg        [h][w] int32 or int64 (SPX_T_I32 / SPX_T_I64), pitch in elements.
+ * boxes_out  [max_label+1, 4] int32 (x1, x2, y1, y2) per label; labels that do
+ *            not occur (and label 0, the background) get (INT_MAX,-1,INT_MAX,-1).
+ *            Labels outside [1, max_label] are ignored.
+ * ======================================================================== */
+int spx_segment_boxes(const void *seg, int seg_kind, int h, int w, int64_t pitch,
+                      int max_label, int32_t *boxes_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

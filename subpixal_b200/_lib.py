@@ -22,7 +22,7 @@ T_F32, T_F64, T_I8, T_I16, T_I32, T_I64 = 0, 1, 2, 3, 4, 5
 
 EXPORTS = ("spx_abi_version", "spx_error_string", "spx_gather_cutouts",
            "spx_cc_workspace_bytes", "spx_cc_fit_stack", "spx_cc_fit_frames",
-           "spx_find_peak")
+           "spx_find_peak", "spx_segment_boxes")
 
 
 class GatherArgs(C.Structure):
@@ -80,6 +80,8 @@ def load():
     lib.spx_find_peak.restype = i32
     lib.spx_find_peak.argtypes = [vp, i32, i32, i32, i32, vp, vp,
                                   i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.spx_segment_boxes.restype = i32
+    lib.spx_segment_boxes.argtypes = [vp, i32, i32, i32, i64, i32, vp, vp]
     if lib.spx_abi_version() != ABI_VERSION:
         raise RuntimeError("subpixal_b200: ABI version mismatch, rebuild the library")
     _lib = lib

@@ -240,3 +240,28 @@ def find_peak_batch(surfaces, mask=None, guess=None, search_box=(0, 0),
                 int(search_box[0]), int(search_box[1]), int(fit_box[0]), int(fit_box[1]),
                 _ptr(xy), _ptr(peak), _ptr(status), _stream()))
     return xy, peak, status
+
+
+MAX_SEG_LABEL = 1 << 24
+
+
+def segment_boxes(seg):
+    """Bounding box of every label of a 2-D int32/int64 CUDA segmentation image in
+    one pass (replaces the per-source scans of reference cutout.py:151-162).
+    Returns an int32 ``[max_label+1, 4]`` CUDA tensor (x1, x2, y1, y2); absent
+    labels have x2 = -1."""
+    require_cuda()
+    lib = L.load()
+    if not seg.is_cuda or seg.dim() != 2 or seg.dtype not in (torch.int32, torch.int64):
+        raise ValueError("seg must be a 2-D int32/int64 CUDA tensor")
+    seg = seg.contiguous()
+    h, w = (int(v) for v in seg.shape)
+    max_label = int(seg.max()) if seg.numel() else 0
+    if max_label > MAX_SEG_LABEL:
+        raise ValueError("segmentation labels above %d are not supported" % MAX_SEG_LABEL)
+    max_label = max(max_label, 0)
+    with torch.cuda.device(seg.device):
+        out = torch.empty((max_label + 1, 4), dtype=torch.int32, device=seg.device)
+        L.check(lib.spx_segment_boxes(_ptr(seg), _KIND[seg.dtype], h, w, w, max_label,
+                                      _ptr(out), _stream()))
+    return out

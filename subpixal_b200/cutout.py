@@ -550,20 +550,13 @@ def _table_columns(catalog):
     return catalog, names
 
 
-def _segment_boxes(seg):
-    """Bounding box of every label of a segmentation image in ONE pass
-    (the reference scans the whole frame once per source, cutout.py:151-162).
-    Returns labels and x1, x2, y1, y2 arrays."""
-    rows, cols = np.nonzero(seg)
-    lab = seg[rows, cols]
-    order = np.argsort(lab, kind='stable')
-    lab, rows, cols = lab[order], rows[order], cols[order]
-    labels, start = np.unique(lab, return_index=True)
-    if labels.size == 0:
-        z = np.zeros(0, dtype=np.int64)
-        return labels, z, z, z, z
-    return (labels, np.minimum.reduceat(cols, start), np.maximum.reduceat(cols, start),
-            np.minimum.reduceat(rows, start), np.maximum.reduceat(rows, start))
+def _segment_boxes(dev_seg):
+    """Bounding box of every label of a segmentation image in ONE GPU pass
+    (``spx_segment_boxes``; the reference scans the whole frame once per source,
+    cutout.py:151-162).  Returns labels and x1, x2, y1, y2 arrays (host)."""
+    tab = batch.segment_boxes(dev_seg).cpu().numpy()
+    labels = np.flatnonzero(tab[:, 1] >= 0)
+    return labels, tab[labels, 0], tab[labels, 1], tab[labels, 2], tab[labels, 3]
 
 
 def create_primary_cutouts(catalog, segmentation_image, imdata, imwcs,
@@ -579,7 +572,10 @@ def create_primary_cutouts(catalog, segmentation_image, imdata, imwcs,
     seg = np.asarray(segmentation_image)
     ny, nx = seg.shape
     pad = _round_pad(pad)
-    labels, lx1, lx2, ly1, ly2 = _segment_boxes(seg)
+    if seg.shape != np.shape(imdata):
+        raise ValueError("segmentation image and image data must have the same shape")
+    dev = _DeviceImage(np.asarray(imdata), imdq, imweight, seg)
+    labels, lx1, lx2, ly1, ly2 = _segment_boxes(dev.seg)
     ids, cat_idx, lab_idx = np.intersect1d(np.asarray(catalog['id']), labels,
                                            return_indices=True)   # cutout.py:139-143
     weights = catalog['weight'] if 'weight' in names else None
@@ -596,7 +592,6 @@ def create_primary_cutouts(catalog, segmentation_image, imdata, imwcs,
                      None if weights is None else weights[ci]))
     if not jobs:
         return []
-    dev = _DeviceImage(np.asarray(imdata), imdq, imweight, seg)
     crops = dev.gather([[b[0], b[1], t[0], t[1]] for _, b, t, _, _ in jobs], 0,
                        src_ids=[j[0] for j in jobs],
                        dq_good_bits=good_bits if imdq is not None else None)

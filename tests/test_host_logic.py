@@ -123,7 +123,7 @@ def test_empty_cutout_and_properties():
     assert np.allclose(c2.pix2world([0.0], [0.0]), [[5.0], [6.0]])
 
 
-def test_slices_and_bit_flags_and_segments():
+def test_slices_and_bit_flags():
     from subpixal_b200 import cutout
     for blc, trc in [((-10, -5), (53, 58)), ((2, 1), (9, 12)), ((90, 95), (120, 99))]:
         ex, ins = cutout._overlap_slices(100, 100, blc, trc)
@@ -133,13 +133,6 @@ def test_slices_and_bit_flags_and_segments():
     assert f(None) is None and f("None") is None and f(6) == 6
     assert f("4,8") == 12 and f("4+8") == 12 and f("~4+8") == ~12 and f("~0") == -1
     assert f(-13) == ~12
-    seg = np.zeros((12, 15), dtype=np.int32)
-    seg[2:5, 3:9] = 7
-    seg[8:11, 1:4] = 2
-    seg[0, 14] = 9
-    lab, x1, x2, y1, y2 = cutout._segment_boxes(seg)
-    assert list(lab) == [2, 7, 9]
-    assert (list(x1), list(x2), list(y1), list(y2)) == ([1, 3, 14], [3, 8, 14], [8, 2, 0], [10, 4, 0])
 
 
 def test_py2round_and_cc_type_codes():

@@ -234,7 +234,10 @@ def bitfield_bad_mask(dq, good_flags):
     dq = np.asarray(dq)
     if good_flags is None:
         return np.zeros(dq.shape, dtype=bool)
-    return (dq & ~np.array(int(good_flags), dtype=dq.dtype)) != 0
+    width = 8 * dq.dtype.itemsize
+    inv = (~int(good_flags)) & ((1 << width) - 1)           # two's complement, dtype width
+    bits = dq.view(np.dtype("u%d" % dq.dtype.itemsize))
+    return (bits & np.array(inv, dtype=bits.dtype)) != 0
 
 
 def crop(data, blc, trc, dq=None, weight=None, mode="strict",

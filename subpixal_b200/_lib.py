@@ -55,12 +55,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SUBPIXAL_B200_LIB", LIB_PATH)   # developer override (kernel variants)
+    if not os.path.exists(path):
         raise RuntimeError(
             "subpixal_b200: CUDA library %s is missing and there is no CPU "
             "fallback. Build it with `python -m subpixal_b200.build` "
-            "(needs nvcc, targets sm_100a)." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+            "(needs nvcc, targets sm_100a)." % path)
+    lib = C.CDLL(path)
     vp, i32, i64, u32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_size_t
     lib.spx_abi_version.restype = i32
     lib.spx_abi_version.argtypes = []

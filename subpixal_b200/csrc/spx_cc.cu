@@ -28,8 +28,27 @@ struct CcParams {
 
 // ---- configurations (one per supported maximum cutout size) -----------------
 //                P   E1  E2 NMAX   T  MINB  W_SMEM R_SMEM INPLACE
-using Cfg32  = CcCfg< 48,  6,  8,  32, 128, 4, true,  true,  true>;
-using Cfg64  = CcCfg< 96, 12,  8,  64, 256, 2, true,  true,  true>;
+// tuning knobs (tools/variant.sh builds variants with -D overrides)
+#ifndef SPX32_E1
+#define SPX32_E1 6
+#endif
+#ifndef SPX32_T
+#define SPX32_T 128
+#endif
+#ifndef SPX32_MINB
+#define SPX32_MINB 6
+#endif
+#ifndef SPX64_E1
+#define SPX64_E1 12
+#endif
+#ifndef SPX64_T
+#define SPX64_T 256
+#endif
+#ifndef SPX64_MINB
+#define SPX64_MINB 2
+#endif
+using Cfg32  = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32_MINB, true,  true,  true>;
+using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, true,  true,  true>;
 using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
 using Cfg256 = CcCfg<384, 24, 16, 256, 256, 1, false, false>;
 

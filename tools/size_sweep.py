@@ -15,12 +15,16 @@ def main():
         pass
     out = []
     gen = torch.Generator(device="cuda").manual_seed(1)
-    for n_side, npairs in ((32, 100000), (64, 25000), (128, 6000), (256, 1500), (48, 40000), (100, 8000)):
+    cases = ((32, 100000), (64, 25000), (128, 6000), (256, 1500), (48, 40000), (100, 8000))
+    if len(sys.argv) > 1:
+        want = [int(v) for v in sys.argv[1].split(",")]
+        cases = tuple(c for c in cases if c[0] in want)
+    for n_side, npairs in cases:
         stack = torch.randn((npairs, 5, n_side, n_side), device=dev, generator=gen)
         yy, xx = torch.meshgrid(torch.arange(n_side, device=dev), torch.arange(n_side, device=dev), indexing="ij")
         blob = 50 * torch.exp(-((xx - n_side / 2) ** 2 + (yy - n_side / 2) ** 2) / 18.0)
         stack += blob
-        for t in ("NCC", "CC", "ZNCC"):
+        for t in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("NCC", "CC", "ZNCC")):
             for _ in range(2):
                 batch.cc_fit_stack(stack, t)
             torch.cuda.synchronize()

@@ -56,6 +56,12 @@ template <> __device__ __forceinline__ bool is_finite<double>(double v) {
     return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
 }
 
+// Each warp owns kRowsPerWarp rows of the cutout and walks them together, so a
+// lane has kRowsPerWarp independent global loads in flight per step (the kernel
+// is latency bound otherwise: one 128-byte request per warp is ~1/4 of what
+// Little's law needs to saturate HBM).
+constexpr int kRowsPerWarp = kGatherRows / (kGatherThreads / 32);     // 4
+
 template <class T>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev a) {
     const int k = blockIdx.y;
@@ -66,39 +72,51 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev 
     const long long off = a.out_offset[k];
     const long long sid = a.src_ids ? a.src_ids[k] : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row_end = min(h, row0 + kGatherRows);
     const T *frame = static_cast<const T *>(a.frame);
     T *out = static_cast<T *>(a.data_out);
     const T fill = T(a.fillval);
-    for (int row = row0 + warp; row < row_end; row += kGatherThreads / 32) {
-        const int yy = y1 + row;
-        const bool inrow = yy >= 0 && yy < a.H;
-        for (int col = lane; col < w; col += 32) {
-            const int xx = x1 + col;
-            const bool inside = inrow && xx >= 0 && xx < a.W;     // cutout.py:742-752
+    const bool aux = a.dq || (a.seg && a.src_ids) || (a.weight && a.weight_out);
+    const int rbase = row0 + warp * kRowsPerWarp;
+    for (int col = lane; col < w; col += 32) {
+        const int xx = x1 + col;
+        const bool incol = xx >= 0 && xx < a.W;
+        T v[kRowsPerWarp];
+        bool inside[kRowsPerWarp];
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {                       // loads first
+            const int row = rbase + r, yy = y1 + row;
+            inside[r] = incol && row < h && yy >= 0 && yy < a.H;      // cutout.py:742-752
+            v[r] = inside[r] ? __ldg(frame + (long long)yy * a.frame_pitch + xx) : fill;
+        }
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            const int row = rbase + r;
+            if (row >= h) break;
             const long long o = off + (long long)row * w + col;
-            T v = inside ? __ldg(frame + (long long)yy * a.frame_pitch + xx) : fill;
-            bool bad = !inside || !is_finite<T>(v);                // cutout.py:755
-            const long long src = (long long)yy * a.W + xx;
-            if (a.dq) {                                            // cutout.py:758-766
-                const long long d = inside ? load_bits(a.dq, src, a.dq_bytes) : 0;
-                if (a.dq_out) store_int(a.dq_out, o, a.dq_bytes, d);
-                if (a.dq_use_bits) bad |= (d & ~a.dq_good_bits) != 0;   // cutout.py:190-193
+            T val = v[r];
+            bool bad = !inside[r] || !is_finite<T>(val);               // cutout.py:755
+            if (aux) {
+                const long long src = (long long)(y1 + row) * a.W + xx;
+                if (a.dq) {                                            // cutout.py:758-766
+                    const long long d = inside[r] ? load_bits(a.dq, src, a.dq_bytes) : 0;
+                    if (a.dq_out) store_int(a.dq_out, o, a.dq_bytes, d);
+                    if (a.dq_use_bits) bad |= (d & ~a.dq_good_bits) != 0;   // cutout.py:190-193
+                }
+                if (a.seg && a.src_ids) {                              // cutout.py:188, 416-419
+                    const long long sg = inside[r] ? load_int(a.seg, src, a.seg_bytes) : 0;
+                    bad |= (sg != sid);
+                }
+                if (a.weight && a.weight_out) {                        // cutout.py:769-779
+                    if (a.weight_f64)
+                        static_cast<double *>(a.weight_out)[o] =
+                            inside[r] ? static_cast<const double *>(a.weight)[src] : 0.0;
+                    else
+                        static_cast<float *>(a.weight_out)[o] =
+                            inside[r] ? static_cast<const float *>(a.weight)[src] : 0.f;
+                }
             }
-            if (a.seg && a.src_ids) {                              // cutout.py:188, 416-419
-                const long long s = inside ? load_int(a.seg, src, a.seg_bytes) : 0;
-                bad |= (s != sid);
-            }
-            if (a.weight && a.weight_out) {                        // cutout.py:769-779
-                if (a.weight_f64)
-                    static_cast<double *>(a.weight_out)[o] =
-                        inside ? static_cast<const double *>(a.weight)[src] : 0.0;
-                else
-                    static_cast<float *>(a.weight_out)[o] =
-                        inside ? static_cast<const float *>(a.weight)[src] : 0.f;
-            }
-            if (a.zero_masked && bad) v = T(0);                    // align.py:661
-            out[o] = v;
+            if (a.zero_masked && bad) val = T(0);                      // align.py:661
+            out[o] = val;
             if (a.mask_out) a.mask_out[o] = bad ? 1 : 0;
         }
     }

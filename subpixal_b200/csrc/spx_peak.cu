@@ -58,12 +58,35 @@ __global__ void __launch_bounds__(kPeakThreads) find_peak_kernel(const PeakParam
     bool found = false;
     if (search) {
         const int bw = sx2 - sx1, cnt = bw * (sy2 - sy1);
-        for (int t = tid; t < cnt; t += kPeakThreads) {
-            const int j = sy1 + t / bw, i = sx1 + t % bw;
-            const int idx = j * p.w + i;
-            if (use_mask && !msk[idx]) continue;
-            BestD c; c.v = double(img[idx]); c.idx = idx;
-            if (!found || bestd_better(c, best)) { best = c; found = true; }
+        if (bw == p.w) {
+            // full-width window: the samples are contiguous, no div/mod, four
+            // independent loads in flight per thread
+            const int base = sy1 * p.w;
+            for (int t0 = tid; t0 < cnt; t0 += 4 * kPeakThreads) {
+                T v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + u * kPeakThreads;
+                    v[u] = t < cnt ? img[base + t] : T(0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + u * kPeakThreads;
+                    if (t >= cnt) break;
+                    const int idx = base + t;
+                    if (use_mask && !msk[idx]) continue;
+                    BestD c; c.v = double(v[u]); c.idx = idx;
+                    if (!found || bestd_better(c, best)) { best = c; found = true; }
+                }
+            }
+        } else {
+            for (int t = tid; t < cnt; t += kPeakThreads) {
+                const int j = sy1 + t / bw, i = sx1 + t % bw;
+                const int idx = j * p.w + i;
+                if (use_mask && !msk[idx]) continue;
+                BestD c; c.v = double(img[idx]); c.idx = idx;
+                if (!found || bestd_better(c, best)) { best = c; found = true; }
+            }
         }
         if (!found) { best.v = -INFINITY; best.idx = 0x7fffffff; }
         // NaN must be able to win over "nothing found": encode absence by idx

@@ -81,8 +81,6 @@ __device__ __forceinline__ Best warp_best(Best b) {
 template <class C>
 struct DevExec {
     double *red;     // [32][8] doubles of reduction scratch in shared memory
-    int *status;     // &PairState::status
-    unsigned tls_word;   // per-thread word that survives between passes
 
     template <class F> __device__ __forceinline__ void par(F f) {
         f(int(threadIdx.x));
@@ -123,16 +121,6 @@ struct DevExec {
         }
         return tot;
     }
-    template <class F> __device__ __forceinline__ void reduce_stats_into(double *acc, F f) {
-        StatPartial tot = reduce_stats(f);
-        if (threadIdx.x == 0) {
-            acc[0] += tot.cnt; acc[1] += tot.sum; acc[2] += tot.sq;
-            acc[3] += tot.rcnt; acc[4] += tot.rsum; acc[5] += tot.rsq;
-            if (tot.flags) atomicOr(status, tot.flags);
-        }
-        __syncthreads();
-    }
-    __device__ __forceinline__ unsigned &tls(int) { return tls_word; }
     template <class F> __device__ __forceinline__ void parts(int n, F f) {
         if (int(threadIdx.x) < n) f(int(threadIdx.x));
         __syncthreads();
@@ -214,8 +202,6 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
 
     DevExec<C> ex;
     ex.red = reinterpret_cast<double *>(smem + L::off_red);
-    ex.status = &c.ps->status;
-    ex.tls_word = 0u;
 
     if (threadIdx.x == 0) build_rrow<C>(rrow);
     __syncthreads();

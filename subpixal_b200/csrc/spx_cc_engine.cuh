@@ -101,8 +101,6 @@ struct PairState {
     int report;            // status bits of the tiles whose NaN/Inf are reported
     int status;
     Best best;             // running argmax over the interlaced surface
-    float post_scale;      // NCC on the fly: 1/(sigma*sigma_ref), applied to the finished surface
-    double acc[6];         // NCC on the fly: cnt, sum, sq, rcnt, rsum, rsq
 };
 
 template <class C>
@@ -247,9 +245,7 @@ SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
     return st;
 }
 
-// post = false: scale folded into R before the transforms; post = true (NCC
-// statistics gathered during the transforms): scale applied to the finished surface
-SPX_HD void stats_finalize(PairState &ps, const StatPartial &t, bool post = false) {
+SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
     ps.status |= t.flags;
     const bool zero = ps.cc_type == SPX_ZNCC;
     double mu = 0.0, sig = NAN, rmu = 0.0, rsig = NAN;
@@ -269,14 +265,11 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t, bool post = fals
     ps.mu_ref = zero ? float(rmu) : 0.f;
     if (!(sc == sc) || !(fabs(sc) < 1e300) || sf == 0.f || rf == 0.f) {
         ps.status |= SPX_S_BAD_NORM;
-    } else if (post) {
-        ps.post_scale = float(sc);
+        ps.rscale = 1.f;
     } else {
         ps.rscale = float(sc);
     }
-    const int nonfinite = SPX_S_NONFINITE_REF | SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
-                          SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
-    if ((t.flags | ps.status) & nonfinite) ps.status |= SPX_S_BAD_NORM;   // NaN/Inf poisons the statistics
+    if (t.flags) ps.status |= SPX_S_BAD_NORM;   // NaN/Inf poisons the statistics
 }
 
 // --------------------------------------------------------------------------
@@ -290,15 +283,8 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t, bool post = fals
 // instead of (n-1)/2, which makes the zero-padding pattern a compile-time
 // property of n1: reference rows exist for n1 < NMAX/E2, image rows for
 // n1 >= NMAX/(2*E2).  No bounds tests, no predicates, minimal address math.
-// OTF (FAST + NCC only): the normalisation statistics of cc.py:131-156 are taken
-// from the pixels as they stream through this pass instead of a separate pass
-// over the tiles.  OTF = 1: first phase pair (remember which of my pixels are
-// non-zero), OTF = 2: second phase pair (union mask complete -> re-read my
-// reference pixels, which are still in cache, and sum them under the mask).
-// `nzbits` is this thread's private mask word; it survives between the passes.
-template <class C, bool FAST, bool IS_REF, int OTF = 0>
-SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
-                   StatPartial *acc = nullptr, unsigned *nzbits = nullptr) {
+template <class C, bool FAST, bool IS_REF>
+SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : ps.nx, ny = FAST ? C::NMAX : ps.ny;
@@ -311,9 +297,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
     constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
     static_assert(!FAST || (C::NMAX / 2) % C::E2 == 0, "fast path needs E2 | NMAX/2");
     int flags = 0;
-    int it = 0;                                   // item counter (bit position block)
-    int icnt = 0, ircnt = 0;
-    for (int wi = warp; wi < nchunk * C::E2; wi += C::NW, ++it) {
+    for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
         const bool active = FAST || i < nx;
         const TileCol ta = tile_col(ps, sa, i, active);
@@ -355,40 +339,6 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
                 vb[n1] = sanitize(vb[n1], pair ? sb : sa, report, flags);
             });
         }
-        if constexpr (OTF != 0) {
-            constexpr int NB = N1_HI - N1_LO;     // my pixels per item
-            unsigned bits = 0u;
-            static_for<N1_LO, N1_HI>([&](auto N1) {
-                constexpr int n1 = decltype(N1)::value;
-                const bool za = va[n1] != 0.f, zb = vb[n1] != 0.f;   // cc.py:134-137
-                const double da = double(va[n1]), db = double(vb[n1]);
-                icnt += (za ? 1 : 0) + (zb ? 1 : 0);
-                acc->sum += da + db;
-                acc->sq += da * da; acc->sq += db * db;
-                bits |= ((za || zb) ? 1u : 0u) << (n1 - N1_LO);
-            });
-            if constexpr (OTF == 1) {
-                *nzbits |= bits << (it * NB);
-            } else {
-                bits |= (*nzbits >> (it * NB)) & ((1u << NB) - 1u);  // union mask, cc.py:150
-                const TileCol tr = tile_col(ps, 0, i, true);
-                const float *pr0 = tr.p + n2 * tr.pitch;
-                float rv[NB];
-                static_for<0, NB>([&](auto K) {
-                    constexpr int k = decltype(K)::value;
-                    rv[k] = ld_f32_last(pr0 + k * rs);
-                });
-                static_for<0, NB>([&](auto K) {
-                    constexpr int k = decltype(K)::value;
-                    const bool m = (bits >> k) & 1u;
-                    float r = rv[k];
-                    if ((f32_bits(r) & 0x7f800000u) == 0x7f800000u) r = 0.f;   // flagged by the ref pass
-                    const double d = double(m ? r : 0.f);               // cc.py:151-154
-                    ircnt += m ? 1 : 0;
-                    acc->rsum += d; acc->rsq += d * d;
-                });
-            }
-        }
         cf x[C::E1];
         if (zncc) {
             static_for<0, C::E1>([&](auto N1) {
@@ -416,7 +366,6 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
             });
         }
     }
-    if constexpr (OTF != 0) { acc->cnt += double(icnt); acc->rcnt += double(ircnt); }
     return flags;
 }
 
@@ -731,7 +680,7 @@ SPX_HD FitSums peak_lane(const PairState &ps, const PeakGeom &g, int lane, LoadF
     FitSums f = fit_zero();
     if (g.mode == 0 && lane < 25) {
         const int dj = lane / 5, di = lane - 5 * dj;
-        const double d = double(ldicc((g.y1 + dj) * (2 * ps.nx) + g.x1 + di) * ps.post_scale);
+        const double d = double(ldicc((g.y1 + dj) * (2 * ps.nx) + g.x1 + di));
         const double u = double(di - 2), v = double(dj - 2);
         f.s0 = d; f.su = u * d; f.sv = v * d; f.suv = u * v * d; f.suu = u * u * d; f.svv = v * v * d;
     }
@@ -818,20 +767,12 @@ SPX_HD void fill_state(PairState &ps, const PairJob &job, int part) {
                   SPX_S_NONFINITE_P11));
     ps.status = job.status0;
     ps.best = best_init();
-    ps.post_scale = 1.f;
-    for (int k = 0; k < 6; ++k) ps.acc[k] = 0.0;
 }
 
 // --------------------------------------------------------------------------
 // reference transform + the two phase pairs (see the data flow at the top)
 // --------------------------------------------------------------------------
-// number of mask bits a thread needs for the on-the-fly statistics
-template <class C> struct OtfBits {
-    static constexpr int ITEMS = ((C::NMAX / 32) * C::E2 + C::NW - 1) / C::NW;
-    static constexpr int VALUE = ITEMS * (C::NMAX / C::E2);
-};
-
-template <class C, bool FAST, bool OTF, class Ex>
+template <class C, bool FAST, class Ex>
 SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
     PairState *ps = c.ps;
     // placement offset of the image tiles and the resulting index shift of the
@@ -861,32 +802,10 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
-        if constexpr (OTF) {
-            ex.reduce_stats_into(ps->acc, [&](int tid) {
-                StatPartial a = stat_zero();
-                unsigned &bits = ex.tls(tid);
-                if (b == 0) {
-                    bits = 0u;
-                    a.flags = c1_pass<C, FAST, false, 1>(c, tid, 1, 2, yoff, cin, &a, &bits);
-                } else {
-                    a.flags = c1_pass<C, FAST, false, 2>(c, tid, 3, 4, yoff, cin, &a, &bits);
-                }
-                return a;
-            });
-            if (b == 1) {
-                ex.single([&]() {
-                    StatPartial t = stat_zero();
-                    t.cnt = ps->acc[0]; t.sum = ps->acc[1]; t.sq = ps->acc[2];
-                    t.rcnt = ps->acc[3]; t.rsum = ps->acc[4]; t.rsq = ps->acc[5];
-                    stats_finalize(*ps, t, true);
-                });
-            }
-        } else {
-            ex.par([&](int tid) {
-                const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin);
-                if (fl) ex.or_status(&ps->status, fl);
-            });
-        }
+        ex.par([&](int tid) {
+            const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin);
+            if (fl) ex.or_status(&ps->status, fl);
+        });
         ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
         if (C::INPLACE) {
             ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
@@ -912,8 +831,6 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 //   single(f)       run f() on one thread, then barrier
 //   parts(n, f)     run f(0..n-1) on n different threads, then barrier
 //   reduce_stats(f) block reduction of f(tid); meaningful in the next single()
-//   reduce_stats_into(acc6, f)  same, added to acc6[0..5] (+ flags into status), barrier
-//   tls(tid)        a 32-bit word private to the thread that survives between passes
 //   reduce_best_into(dst, f)  block argmax of f(tid) merged into *dst, barrier
 //   warp_fit(lane_f, final_f) one warp: sum lane_f(lane) over 32 lanes, then
 //                   final_f(sum) on one lane, then barrier
@@ -927,24 +844,16 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     PairState *ps = c.ps;
     ex.parts(6, [&](int part) { fill_state(*ps, job, part); });
 
-    const bool fast = job.ny == C::NMAX && job.nx == C::NMAX && job.x1 >= 0 && job.y1 >= 0 &&
-                      job.x1 + job.nx <= job.W && job.y1 + job.ny <= job.H;
-    // NCC on full interior cutouts: statistics on the fly (needs <= 32 mask bits per thread)
-    const bool otf = fast && job.cc_type == SPX_NCC && OtfBits<C>::VALUE <= 32;
-
     // ---- normalisation statistics (cc.py:131-156) ----------------------
-    if (job.cc_type != SPX_CC && !otf) {
+    if (job.cc_type != SPX_CC) {
         StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(*ps, tid); });
         ex.single([&]() { stats_finalize(*ps, tot); });
     }
 
-    if (otf) {
-        if constexpr (OtfBits<C>::VALUE <= 32) run_transforms<C, true, true>(c, ex);
-    } else if (fast) {
-        run_transforms<C, true, false>(c, ex);
-    } else {
-        run_transforms<C, false, false>(c, ex);
-    }
+    const bool fast = job.ny == C::NMAX && job.nx == C::NMAX && job.x1 >= 0 && job.y1 >= 0 &&
+                      job.x1 + job.nx <= job.W && job.y1 + job.ny <= job.H;
+    if (fast) run_transforms<C, true>(c, ex);
+    else run_transforms<C, false>(c, ex);
 
     // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
     {
@@ -967,14 +876,11 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
             const int st = ps->status;
             const int nanbits = SPX_S_NONFINITE_REF | SPX_S_BAD_NORM | SPX_S_NONFINITE_P00 |
                                 SPX_S_NONFINITE_P10 | SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
-            const int ne = 4 * ps->ny * ps->nx;
-            const float sc = ps->post_scale;
             if (st & nanbits) {
+                const int ne = 4 * ps->ny * ps->nx;
                 union { unsigned u; float f; } qnan; qnan.u = 0x7fc00000u;
                 for (int i = tid; i < ne; i += C::T)
-                    c.icc[i] = icc_is_nan(*ps, st, i) ? qnan.f : c.icc[i] * sc;
-            } else if (sc != 1.f) {
-                for (int i = tid; i < ne; i += C::T) c.icc[i] *= sc;
+                    if (icc_is_nan(*ps, st, i)) c.icc[i] = qnan.f;
             }
         });
     }

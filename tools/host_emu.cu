@@ -28,15 +28,6 @@ struct HostExec {
         for (int t = 0; t < C::T; ++t) { StatPartial s = f(t); stat_merge(tot, s); }
         return tot;
     }
-    int *status;
-    std::vector<unsigned> words = std::vector<unsigned>(C::T, 0u);
-    unsigned &tls(int tid) { return words[tid]; }
-    template <class F> void reduce_stats_into(double *acc, F f) {
-        StatPartial tot = reduce_stats(f);
-        acc[0] += tot.cnt; acc[1] += tot.sum; acc[2] += tot.sq;
-        acc[3] += tot.rcnt; acc[4] += tot.rsum; acc[5] += tot.rsq;
-        *status |= tot.flags;
-    }
     template <class F> void parts(int n, F f) { for (int t = 0; t < n; ++t) f(t); }
     template <class F> void reduce_best_into(Best *dst, F f) {
         for (int t = 0; t < C::T; ++t) { Best b = f(t); if (best_better(b, *dst)) *dst = b; }
@@ -60,7 +51,6 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
     Ctx<C> c;
     c.W = W.data(); c.S = S.data(); c.R = R.data(); c.rrow = rrow.data(); c.ps = &ps;
     HostExec<C> ex;
-    ex.status = &ps.status;
     const size_t tile = size_t(ny) * nx;
     for (int p = 0; p < n; ++p) {
         c.icc = icc + size_t(p) * 4 * tile;

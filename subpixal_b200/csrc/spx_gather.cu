@@ -81,17 +81,12 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev 
         const int xx = x1 + col;
         const bool incol = xx >= 0 && xx < a.W;
         T v[kRowsPerWarp];
-        long long dqv[kRowsPerWarp], sgv[kRowsPerWarp];
         bool inside[kRowsPerWarp];
-        const bool want_dq = a.dq != nullptr, want_seg = a.seg && a.src_ids;
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) {                       // loads first
             const int row = rbase + r, yy = y1 + row;
             inside[r] = incol && row < h && yy >= 0 && yy < a.H;      // cutout.py:742-752
             v[r] = inside[r] ? __ldg(frame + (long long)yy * a.frame_pitch + xx) : fill;
-            const long long src = (long long)yy * a.W + xx;
-            dqv[r] = (want_dq && inside[r]) ? load_bits(a.dq, src, a.dq_bytes) : 0;
-            sgv[r] = (want_seg && inside[r]) ? load_int(a.seg, src, a.seg_bytes) : 0;
         }
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) {
@@ -102,13 +97,14 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev 
             bool bad = !inside[r] || !is_finite<T>(val);               // cutout.py:755
             if (aux) {
                 const long long src = (long long)(y1 + row) * a.W + xx;
-                if (want_dq) {                                         // cutout.py:758-766
-                    const long long d = dqv[r];
+                if (a.dq) {                                            // cutout.py:758-766
+                    const long long d = inside[r] ? load_bits(a.dq, src, a.dq_bytes) : 0;
                     if (a.dq_out) store_int(a.dq_out, o, a.dq_bytes, d);
                     if (a.dq_use_bits) bad |= (d & ~a.dq_good_bits) != 0;   // cutout.py:190-193
                 }
-                if (want_seg) {                                        // cutout.py:188, 416-419
-                    bad |= (sgv[r] != sid);
+                if (a.seg && a.src_ids) {                              // cutout.py:188, 416-419
+                    const long long sg = inside[r] ? load_int(a.seg, src, a.seg_bytes) : 0;
+                    bad |= (sg != sid);
                 }
                 if (a.weight && a.weight_out) {                        // cutout.py:769-779
                     if (a.weight_f64)

@@ -176,7 +176,7 @@ def physical_gpu_index(local_rank):
 
 
 # ----------------------------------------------------------------------------
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU path (oracle port) on all host cores."""
     if rank != 0:
         return
@@ -220,7 +220,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -255,8 +255,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout must carry exactly ONE JSON line: libraries that print to fd 1
+    # (e.g. NCCL's version banner) are sent to stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
@@ -438,7 +449,7 @@ def main():
             "gpu_launches": args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

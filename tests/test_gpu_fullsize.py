@@ -88,3 +88,50 @@ def test_config3_128_masked():
     bad = (st.cpu().numpy() & 0x3e) != 0
     assert bad.any()
     assert np.all(sh.cpu().numpy()[bad] == np.array([-63.0, -63.0]))
+
+
+def test_config4_workflow_recovers_frame_transform():
+    """Reduced config 4: shifts of 20 000 sources on a 4096x4096 frame feed the
+    linear-transformation fit, which must recover the injected misalignment."""
+    from subpixal_b200 import align, batch, synthetic as syn
+    shift, rot = (0.31, -0.17), 8e-5
+    sc = syn.make_scene(20000, 4096, 4096, 64, seed=20244)
+    frames, truth = syn.make_frames(sc, "cuda", shift=shift, rot=rot)
+    boxes = syn.make_boxes(sc)
+    sh, pk, st, _ = batch.cc_fit_frames(frames, torch.from_numpy(boxes).cuda(), 64, 64, "NCC")
+    sh = sh.cpu().numpy()
+    xy = np.stack([sc["x"], sc["y"]], axis=1)
+    centre = np.array([(4096 - 1) / 2.0, (4096 - 1) / 2.0])
+    fit = align.iter_linear_fit(xy, xy + sh, fitgeom="rscale", center=centre, nclip=3, sigma=3.0)
+    assert np.allclose(fit["offset"], shift, atol=5e-3)
+    assert abs(np.deg2rad(fit["rot"]) - rot) < 3e-6 and abs(fit["scale"][0] - 1.0) < 3e-6
+    # the same fit fed with the CPU oracle's shifts on a subsample agrees
+    idx = np.arange(0, 20000, 40)
+    stack = syn.cut_stack(frames.cpu().numpy(), boxes[idx])
+    ref = np.array([orc.find_displacement(*s, cc_type="NCC") for s in stack])
+    assert np.max(np.abs(ref - sh[idx])) < 1e-4
+    f_cpu = align.iter_linear_fit(xy[idx], xy[idx] + ref, fitgeom="rscale", center=centre)
+    f_gpu = align.iter_linear_fit(xy[idx], xy[idx] + sh[idx], fitgeom="rscale", center=centre)
+    assert np.allclose(f_cpu["offset"], f_gpu["offset"], atol=1e-5)
+    assert np.allclose(f_cpu["matrix"], f_gpu["matrix"], atol=1e-8)
+
+
+def test_100k_boxes_128_properties():
+    """Config-3 sized batch (100 000 pairs of 128x128) through the fused path:
+    determinism, independence of the pairs, edge boxes, finite results."""
+    from subpixal_b200 import batch, synthetic as syn
+    sc = syn.make_scene(5000, 2048, 4096, 128, seed=20245)
+    frames, _ = syn.make_frames(sc, "cuda")
+    base = torch.from_numpy(syn.make_boxes(sc)).cuda()
+    gen = torch.Generator("cuda").manual_seed(5)
+    jit = torch.randint(-40, 41, (100000, 2), device="cuda", generator=gen, dtype=torch.int32)
+    boxes = base[torch.randint(0, 5000, (100000,), device="cuda", generator=gen)].clone()
+    boxes[:, [0, 2]] += jit[:, :1]
+    boxes[:, [1, 3]] += jit[:, 1:]
+    sh, pk, st, _ = batch.cc_fit_frames(frames, boxes, 128, 128, "NCC")
+    assert bool(torch.isfinite(sh).all()) and int((st & 0x43f).max()) == 0
+    sh2, pk2, _, _ = batch.cc_fit_frames(frames, boxes, 128, 128, "NCC")
+    assert torch.equal(sh, sh2) and torch.equal(pk, pk2)
+    sub = torch.arange(0, 100000, 97, device="cuda")
+    sh3, pk3, _, _ = batch.cc_fit_frames(frames, boxes[sub], 128, 128, "NCC")
+    assert torch.equal(sh3, sh[sub]) and torch.equal(pk3, pk[sub])

@@ -177,9 +177,13 @@ SPX_HD void stat_merge(StatPartial &a, const StatPartial &b) {
 
 // non-finite pixels become 0; they raise the tile's status bit unless the
 // caller asked for masked-pixel zeroing (align.py:661)
+// internal status bit: a non-finite pixel was seen (reported or silently zeroed);
+// never leaves the kernel
+constexpr int kSawNonFinite = 0x40000000;
+
 SPX_HD float sanitize(float v, int s, int report, int &flags) {
     if ((f32_bits(v) & 0x7f800000u) == 0x7f800000u) {
-        flags |= report & (SPX_S_NONFINITE_REF << s);
+        flags |= kSawNonFinite | (report & (SPX_S_NONFINITE_REF << s));
         v = 0.f;
     }
     return v;
@@ -269,7 +273,7 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
     } else {
         ps.rscale = float(sc);
     }
-    if (t.flags) ps.status |= SPX_S_BAD_NORM;   // NaN/Inf poisons the statistics
+    if (t.flags & ~kSawNonFinite) ps.status |= SPX_S_BAD_NORM;   // NaN/Inf poisons the statistics
 }
 
 // --------------------------------------------------------------------------
@@ -283,7 +287,9 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
 // instead of (n-1)/2, which makes the zero-padding pattern a compile-time
 // property of n1: reference rows exist for n1 < NMAX/E2, image rows for
 // n1 >= NMAX/(2*E2).  No bounds tests, no predicates, minimal address math.
-template <class C, bool FAST, bool IS_REF>
+// CHECK = false: the statistics pass has already scanned these tiles and found
+// them finite, so the NaN/Inf tracking is skipped.
+template <class C, bool FAST, bool IS_REF, bool CHECK = true>
 SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
@@ -326,13 +332,15 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
         });
         // one cheap test for "any NaN/Inf among my pixels": max of |bits|
         unsigned worst = 0u;
-        static_for<N1_LO, N1_HI>([&](auto N1) {
-            constexpr int n1 = decltype(N1)::value;
-            const unsigned ua = f32_bits(va[n1]) & 0x7fffffffu, ub = f32_bits(vb[n1]) & 0x7fffffffu;
-            worst = worst > ua ? worst : ua;
-            if (pair) worst = worst > ub ? worst : ub;
-        });
-        if (worst >= 0x7f800000u) {                          // rare
+        if constexpr (CHECK) {
+            static_for<N1_LO, N1_HI>([&](auto N1) {
+                constexpr int n1 = decltype(N1)::value;
+                const unsigned ua = f32_bits(va[n1]) & 0x7fffffffu, ub = f32_bits(vb[n1]) & 0x7fffffffu;
+                worst = worst > ua ? worst : ua;
+                if (pair) worst = worst > ub ? worst : ub;
+            });
+        }
+        if (CHECK && worst >= 0x7f800000u) {                 // rare
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
                 va[n1] = sanitize(va[n1], sa, report, flags);
@@ -690,7 +698,7 @@ SPX_HD FitSums peak_lane(const PairState &ps, const PeakGeom &g, int lane, LoadF
 SPX_HD void peak_final(const PairState &ps, const PeakGeom &g, const FitSums &f,
                        double *shift2, int *peak, int *status) {
     const int h2 = 2 * ps.ny, w2 = 2 * ps.nx;
-    int st = ps.status;
+    int st = ps.status & ~kSawNonFinite;
     double x = double(g.imax), y = double(g.jmax);
     if (g.mode != 0) {
         st |= (g.imax == 0 || g.jmax == 0) ? SPX_S_PEAK_EDGE : SPX_S_FIT_NONFINITE;
@@ -715,7 +723,7 @@ SPX_HD void peak_final(const PairState &ps, const PeakGeom &g, const FitSums &f,
     shift2[0] = 0.5 * x - double(xc4);                                   // cc.py:92-93
     shift2[1] = 0.5 * y - double(yc4);
     *peak = g.idx;
-    *status = st;
+    *status = st & ~kSawNonFinite;
 }
 
 // value the reference's surface has at flat index idx when inputs were
@@ -772,7 +780,7 @@ SPX_HD void fill_state(PairState &ps, const PairJob &job, int part) {
 // --------------------------------------------------------------------------
 // reference transform + the two phase pairs (see the data flow at the top)
 // --------------------------------------------------------------------------
-template <class C, bool FAST, class Ex>
+template <class C, bool FAST, bool CHECK, class Ex>
 SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
     PairState *ps = c.ps;
     // placement offset of the image tiles and the resulting index shift of the
@@ -785,7 +793,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 
     // ---- reference image -> conj(R) * scale, half spectrum ---------------
     ex.par([&](int tid) {
-        const int fl = c1_pass<C, FAST, true>(c, tid, 0, -1, 0, 0);
+        const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0);
         if (fl) ex.or_status(&ps->status, fl);
     });
     ex.par([&](int tid) { c2_pass<C>(c, tid, 0); });
@@ -803,7 +811,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
         ex.par([&](int tid) {
-            const int fl = c1_pass<C, FAST, false>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin);
+            const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin);
             if (fl) ex.or_status(&ps->status, fl);
         });
         ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
@@ -852,8 +860,16 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
 
     const bool fast = job.ny == C::NMAX && job.nx == C::NMAX && job.x1 >= 0 && job.y1 >= 0 &&
                       job.x1 + job.nx <= job.W && job.y1 + job.ny <= job.H;
-    if (fast) run_transforms<C, true>(c, ex);
-    else run_transforms<C, false>(c, ex);
+    // tiles already scanned by the statistics pass and found finite -> no NaN tracking
+    const int nonfinite = SPX_S_NONFINITE_REF | SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
+                          SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
+    const bool check = job.cc_type == SPX_CC || (ps->status & (nonfinite | kSawNonFinite)) != 0;
+    if (fast) {
+        if (check) run_transforms<C, true, true>(c, ex);
+        else run_transforms<C, true, false>(c, ex);
+    } else {
+        run_transforms<C, false, true>(c, ex);
+    }
 
     // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
     {

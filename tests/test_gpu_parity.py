@@ -290,3 +290,42 @@ def test_cabi_error_codes():
     assert lib.spx_find_peak(p, 0, 1, 8, 8, z, z, 0, 0, 99, 5, p, p, p, z) == L.E_UNSUPPORTED
     with pytest.raises(L.SubpixalError):
         L.check(L.E_WORKSPACE)
+
+
+def test_randomised_shapes_masks_and_nans():
+    """60 seeded random problems: arbitrary (ny, nx) in [3, 140], random cc_type,
+    random zero masks, occasional NaN / Inf in a random tile - every one must match
+    the oracle (shift, peak index, NaN pattern of the surface)."""
+    from subpixal_b200 import batch
+    rng = np.random.default_rng(424242)
+    for case in range(60):
+        ny, nx = (int(v) for v in rng.integers(3, 141, 2))
+        if case % 5 == 0:
+            ny = nx = int(rng.choice([32, 64, 128]))          # exercise the full-tile fast path
+        t = CC_TYPES[int(rng.integers(0, 3))]
+        st, _ = orc.random_pairs(2, ny, nx, seed=int(rng.integers(1 << 30)),
+                                 masked=bool(rng.integers(0, 2)))
+        if rng.uniform() < 0.3:
+            st[0, 1:, : max(1, ny // 4), :] = 0.0               # zero band in all phases
+        poisoned = rng.uniform() < 0.25
+        if poisoned:
+            st[1, int(rng.integers(0, 5)), int(rng.integers(0, ny)), int(rng.integers(0, nx))] = \
+                [np.nan, np.inf, -np.inf][int(rng.integers(0, 3))]
+        sh, pk, status, icc = batch.cc_fit_stack(torch.from_numpy(st).cuda(), t, want_icc=True)
+        sh, pk, icc = sh.cpu().numpy(), pk.cpu().numpy(), icc.cpu().numpy()
+        for k in range(2):
+            dx, dy, oicc, _ = _oracle(st[k], t)
+            with np.errstate(all="ignore"):
+                oam = int(np.argmax(oicc.astype(np.float64)))
+            tag = (case, ny, nx, t, k, poisoned)
+            assert np.array_equal(np.isnan(icc[k]), np.isnan(oicc)), tag
+            if np.isnan(oicc).all():
+                assert (sh[k, 0], sh[k, 1]) == (dx, dy) and pk[k] == oam, tag
+                continue
+            fin = ~np.isnan(oicc)
+            assert np.linalg.norm(icc[k][fin] - oicc[fin]) <= ICC_L2_TOL * np.linalg.norm(oicc[fin]), tag
+            if pk[k] != oam:             # only a numerical near-tie may move the peak
+                srt = np.sort(oicc[fin].ravel())
+                assert (srt[-1] - srt[-2]) <= 1e-5 * abs(srt[-1]), tag
+                continue
+            assert abs(sh[k, 0] - dx) < 1e-4 and abs(sh[k, 1] - dy) < 1e-4, tag

@@ -6,10 +6,13 @@
 // cross-power, correlation rows) lives in shared memory (or, for cutouts too
 // large for one SM, in a per-CTA slab that stays L2 resident), and only the
 // (dx, dy) pair goes back to HBM unless the caller asks for the surface.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/subpixal_b200.h"
 #include "spx_cc_engine.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace spx {
 
@@ -49,7 +52,14 @@ struct CcParams {
 #endif
 using Cfg32  = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32_MINB, true,  true,  true>;
 using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, true,  true,  true>;
+#ifndef SPX128_CLUSTER
+#define SPX128_CLUSTER 1
+#endif
+#if SPX128_CLUSTER
+using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, true,  true,  false, 2>;   // 2-CTA cluster, DSMEM
+#else
 using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
+#endif
 using Cfg256 = CcCfg<384, 24, 16, 256, 256, 1, false, false>;
 
 template <class C> struct Layout {
@@ -57,13 +67,17 @@ template <class C> struct Layout {
     static constexpr size_t off_ps = 0;
     static constexpr size_t off_red = 256;                       // reductions
     static constexpr size_t red_bytes = 32 * 8 * 8;              // [32 warps][8] doubles
-    static constexpr size_t off_rrow = off_red + red_bytes;
+    static constexpr size_t off_xchg = off_red + red_bytes;       // Xchg (cluster mode)
+    static constexpr size_t off_rrow = off_xchg + 256;
     static constexpr size_t rrow_bytes = ((C::RH * 2 + 15) / 16) * 16;
-    static constexpr size_t off_S = off_rrow + rrow_bytes;
+    static constexpr size_t off_xrow = off_rrow + rrow_bytes;
+    static constexpr size_t xrow_bytes = C::CL == 2 ? ((C::P + 15) / 16) * 16 : 0;
+    static constexpr size_t off_S = off_xrow + xrow_bytes;
     static constexpr size_t off_W = off_S + C::S_ELEMS * 8;
     static constexpr size_t off_R = off_W + (C::W_SMEM ? C::W_ELEMS * 8 : 0);
     static constexpr size_t total = off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0);
     static_assert(sizeof(PairState) <= 256, "PairState must fit its slot");
+    static_assert(sizeof(Xchg) <= 256, "Xchg must fit its slot");
 };
 
 __device__ __forceinline__ Best warp_best(Best b) {
@@ -156,6 +170,8 @@ struct DevExec {
         }
         __syncthreads();
     }
+    __device__ __forceinline__ void cluster_sync() { cg::this_cluster().sync(); }
+    __device__ __forceinline__ void global_fence() { __threadfence(); }
     __device__ __forceinline__ void or_status(int *p, int v) { atomicOr(p, v); }
     __device__ __forceinline__ float load_icc(const float *p) { return __ldcg(p); }
 };
@@ -189,7 +205,11 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     extern __shared__ __align__(16) unsigned char smem[];
     using L = Layout<C>;
     uint16_t *rrow = reinterpret_cast<uint16_t *>(smem + L::off_rrow);
-    unsigned char *slab = prm.workspace + size_t(blockIdx.x) * prm.slab_bytes;
+    uint16_t *xrow = reinterpret_cast<uint16_t *>(smem + L::off_xrow);
+    // one pair per CTA, or per cluster of CL CTAs
+    const int rank = C::CL == 2 ? int(cg::this_cluster().block_rank()) : 0;
+    const int unit = blockIdx.x / C::CL, nunits = gridDim.x / C::CL;
+    unsigned char *slab = prm.workspace + size_t(unit) * prm.slab_bytes;
 
     Ctx<C> c;
     c.S = reinterpret_cast<cf *>(smem + L::off_S);
@@ -198,16 +218,32 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     c.R = C::R_SMEM ? reinterpret_cast<cf *>(smem + L::off_R)
                     : reinterpret_cast<cf *>(slab + prm.off_r);
     c.rrow = rrow;
+    c.xrow = C::CL == 2 ? xrow : nullptr;
     c.ps = reinterpret_cast<PairState *>(smem + L::off_ps);
+    c.rank = rank;
+    c.col_lo = rank * C::NXL;
+    c.xl = reinterpret_cast<Xchg *>(smem + L::off_xchg);
+    c.Wpeer = nullptr; c.xp = nullptr;
+    if (C::CL == 2) {
+        cg::cluster_group cluster = cg::this_cluster();
+        c.Wpeer = cluster.map_shared_rank(c.W, rank ^ 1);
+        c.xp = cluster.map_shared_rank(c.xl, rank ^ 1);
+    }
 
     DevExec<C> ex;
     ex.red = reinterpret_cast<double *>(smem + L::off_red);
 
-    if (threadIdx.x == 0) build_rrow<C>(rrow);
+    __shared__ int s_nrrow;
+    if (threadIdx.x == 0) {
+        s_nrrow = build_rrow<C>(rrow, rank);
+        if (C::CL == 2) build_xrow<C>(xrow, rank);
+    }
     __syncthreads();
+    c.n_rrow = s_nrrow;
+    if (C::CL == 2) cg::this_cluster().sync();     // the peer is resident: DSMEM may be used
 
     const size_t icc_elems = size_t(4) * prm.ny * prm.nx;
-    for (int p = blockIdx.x; p < prm.n; p += gridDim.x) {
+    for (int p = unit; p < prm.n; p += nunits) {
         c.icc = prm.icc_out ? prm.icc_out + size_t(p) * icc_elems
                             : reinterpret_cast<float *>(slab + prm.off_icc);
         PairJob job;
@@ -222,13 +258,14 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
         job.pitch = prm.pitch; job.H = prm.H; job.W = prm.W;
         job.ny = prm.ny; job.nx = prm.nx; job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
-        prefetch_pair<C>(prm, p + gridDim.x);
+        if (rank == 0) prefetch_pair<C>(prm, p + nunits);
         process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
     }
+    if (C::CL == 2) cg::this_cluster().sync();     // do not exit while the peer may still read my W
 }
 
 // ---- host side ------------------------------------------------------------------
-struct SlabPlan { size_t off_icc, off_w, off_r, bytes; int max_ctas_per_sm; };
+struct SlabPlan { size_t off_icc, off_w, off_r, bytes; int max_ctas_per_sm, cluster; };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -241,6 +278,7 @@ static SlabPlan plan_slab(int ny, int nx, bool want_icc) {
     s.off_r = o;   if (!C::R_SMEM) o += align_up(C::R_ELEMS * 8, 256);
     s.bytes = align_up(o, 256);
     s.max_ctas_per_sm = C::MINB;
+    s.cluster = C::CL;
     return s;
 }
 
@@ -272,8 +310,9 @@ static SlabPlan plan_for(int cfg, int ny, int nx, bool want_icc) {
     }
 }
 
-static int grid_for(int n, const SlabPlan &sp) {
-    const long long cap = (long long)num_sms() * sp.max_ctas_per_sm;
+// number of pairs in flight = CTAs (or clusters) in the persistent grid
+static int units_for(int n, const SlabPlan &sp) {
+    const long long cap = (long long)num_sms() * sp.max_ctas_per_sm / sp.cluster;
     return int(n < cap ? n : cap);
 }
 
@@ -283,8 +322,20 @@ static int launch(CcParams &prm, const SlabPlan &sp, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(cc_fit_kernel<C>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
-    const int grid = grid_for(prm.n, sp);
-    cc_fit_kernel<C><<<grid, C::T, smem, stream>>>(prm);
+    const int grid = units_for(prm.n, sp) * C::CL;
+    if (C::CL == 1) {
+        cc_fit_kernel<C><<<grid, C::T, smem, stream>>>(prm);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::T);
+        cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, cc_fit_kernel<C>, prm);
+        if (e != cudaSuccess) return int(e);
+    }
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : int(e);
 }
@@ -298,7 +349,7 @@ static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *
     if (prm.n == 0) return 0;
     if (prm.cc_type != SPX_NCC && prm.cc_type != SPX_ZNCC) prm.cc_type = SPX_CC;  // cc.py:108
     const SlabPlan sp = plan_for(cfg, prm.ny, prm.nx, prm.icc_out != nullptr);
-    const size_t need = sp.bytes * size_t(grid_for(prm.n, sp));
+    const size_t need = sp.bytes * size_t(units_for(prm.n, sp));
     if (need > 0 && (!workspace || workspace_bytes < need)) return SPX_E_WORKSPACE;
     prm.workspace = static_cast<unsigned char *>(workspace);
     prm.slab_bytes = sp.bytes;
@@ -320,7 +371,7 @@ size_t spx_cc_workspace_bytes(int n, int ny, int nx, int want_icc) {
     const int cfg = spx::pick_cfg(ny, nx);
     if (!cfg || n <= 0 || ny < 1 || nx < 1) return 0;
     const spx::SlabPlan sp = spx::plan_for(cfg, ny, nx, want_icc != 0);
-    return sp.bytes * size_t(spx::grid_for(n, sp));
+    return sp.bytes * size_t(spx::units_for(n, sp));
 }
 
 int spx_cc_fit_stack(const float *ref, const float *im00, const float *im10,

@@ -63,21 +63,34 @@ SPX_TW(48) SPX_TW(96) SPX_TW(192) SPX_TW(384)
 // rows - three barriers per row stage and no separate scratch.  Otherwise W is
 // P x (NMAX+1) and the row stage goes through a 32-row scratch S, batch by batch
 // (used when W lives in global memory).
+//
+// CL = 2: one pair is processed by a thread-block cluster of two CTAs.  W is
+// split by COLUMNS (each CTA holds all P rows of NMAX/2 columns in its shared
+// memory, so the column passes are purely local); the row stage of row r is done
+// by the CTA that owns r, which pulls the other half of the row out of the peer's
+// shared memory (DSMEM) and pushes the results back.  Rows are assigned by the
+// parity of q(r) = min(ky, P-ky), so that each CTA only needs the R rows of its
+// own parity (half of R).
 template <int P_, int E1_, int E2_, int NMAX_, int T_, int MINB_, bool WSM_, bool RSM_,
-          bool INPLACE_ = false>
+          bool INPLACE_ = false, int CL_ = 1>
 struct CcCfg {
     static constexpr int P = P_, E1 = E1_, E2 = E2_, NMAX = NMAX_, T = T_, MINB = MINB_;
     static constexpr bool W_SMEM = WSM_, R_SMEM = RSM_, INPLACE = INPLACE_;
+    static constexpr int CL = CL_;
     static constexpr int NW = T / 32;
-    static constexpr int WP = INPLACE ? P + 1 : NMAX + 1;   // pitch of W (complex), odd
+    static constexpr int NXL = NMAX / CL;    // columns of W held by one CTA
+    static constexpr int WP = INPLACE ? P + 1 : NXL + 1;    // pitch of W (complex), odd
     static constexpr int SP = P + 1;         // pitch of the row scratch, odd
     static constexpr int RP = P + 1;         // pitch of R, odd
     static constexpr int RH = P / 2 + 1;     // rows of R (half spectrum)
+    static constexpr int RHL = (RH + CL - 1) / CL;   // ... held by one CTA
     static constexpr int BATCH = 32;         // rows per row-op batch (= lanes)
-    static constexpr int NCHUNK = (P + 31) / 32, RCHUNK = (RH + 31) / 32;
+    static constexpr int NCHUNK = (P / CL + 31) / 32, RCHUNK = (RHL + 31) / 32;
     static constexpr size_t W_ELEMS = size_t(P) * WP;
     static constexpr size_t S_ELEMS = INPLACE ? 0 : size_t(BATCH) * SP;
-    static constexpr size_t R_ELEMS = size_t(RH) * RP;
+    static constexpr size_t R_ELEMS = size_t(RHL) * RP;
+    static_assert(CL == 1 || (CL == 2 && !INPLACE && WSM_ && RSM_ && P % 64 == 0),
+                  "cluster mode: staged row stage, W and R in shared memory");
     static_assert(E1 * E2 == P, "P = E1*E2");
     static_assert(P % 2 == 0 && NMAX % 2 == 0, "even sizes");
     static_assert(T % 32 == 0, "whole warps");
@@ -103,13 +116,35 @@ struct PairState {
     Best best;             // running argmax over the interlaced surface
 };
 
+// Values the two CTAs of a cluster hand to each other (each CTA writes slot
+// [rank] of BOTH copies, then a cluster barrier, then reads its local copy).
+struct Xchg {
+    double stat[2][8];
+    float bestv[2];
+    int besti[2];
+    int status[2];
+};
+
 template <class C>
 struct Ctx {
     cf *W, *S, *R;
     float *icc;            // [2ny][2nx] interlaced surface of this pair
-    const uint16_t *rrow;  // rows of W (scrambled ky order) with ky <= P/2
+    const uint16_t *rrow;  // rows of W (scrambled ky order) with ky <= P/2 (of my parity)
     PairState *ps;
+    // cluster mode (CL == 2); rank = 0, col_lo = 0 and null pointers otherwise
+    int rank, col_lo, n_rrow;
+    cf *Wpeer;             // the peer CTA's W (distributed shared memory)
+    const uint16_t *xrow;  // rows of W whose row stage is mine
+    Xchg *xl, *xp;         // local / peer exchange block
 };
+
+// number of tile columns held by this CTA
+template <class C>
+SPX_HD int local_cols(const Ctx<C> &c, int nx) {
+    if (C::CL == 1) return nx;
+    int n = nx - c.col_lo;
+    return n < 0 ? 0 : (n > C::NXL ? C::NXL : n);
+}
 
 // Warp index as a value the compiler KNOWS is warp-uniform (so that n2 / k1,
 // the predicates and the twiddle addresses derived from it live in uniform
@@ -190,10 +225,16 @@ SPX_HD float sanitize(float v, int s, int report, int &flags) {
 }
 
 template <class C>
-SPX_HD StatPartial stats_thread(const PairState &ps, int tid) {
+SPX_HD StatPartial stats_thread(const Ctx<C> &c, int tid) {
+    const PairState &ps = *c.ps;
     StatPartial st = stat_zero();
     const int warp = warp_of(tid), lane = tid & 31;
-    const int report = ps.report, ylo = ps.ylo, yhi = ps.yhi, xlo = ps.xlo, xhi = ps.xhi;
+    const int report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
+    int xlo = ps.xlo, xhi = ps.xhi;
+    if (C::CL == 2) {                       // my half of the columns
+        if (xlo < c.col_lo) xlo = c.col_lo;
+        if (xhi > c.col_lo + C::NXL) xhi = c.col_lo + C::NXL;
+    }
     const int pitch = int(ps.pitch[0]);
     const long long step = (long long)C::NW * pitch;
     int cnt = 0, rcnt = 0;
@@ -293,9 +334,9 @@ template <class C, bool FAST, bool IS_REF, bool CHECK = true>
 SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = FAST ? C::NMAX : ps.nx, ny = FAST ? C::NMAX : ps.ny;
+    const int nx = FAST ? C::NXL : local_cols(c, ps.nx), ny = FAST ? C::NMAX : ps.ny;
     const int report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
-    const int nchunk = (nx + 31) >> 5;
+    const int nchunk = (nx + 31) >> 5;            // nx, i: LOCAL columns from here on
     const bool pair = !IS_REF;
     const bool zncc = ps.cc_type == SPX_ZNCC;
     const float mu = ps.mu, mu_ref = ps.mu_ref;
@@ -306,8 +347,8 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
         const bool active = FAST || i < nx;
-        const TileCol ta = tile_col(ps, sa, i, active);
-        const TileCol tb = tile_col(ps, pair ? sb : sa, i, active && pair);
+        const TileCol ta = tile_col(ps, sa, c.col_lo + i, active);
+        const TileCol tb = tile_col(ps, pair ? sb : sa, c.col_lo + i, active && pair);
         const int ybase = n2 - yoff;
         const int rs = C::E2 * ta.pitch;                     // elements between loads
         const float *pa0 = ta.p + ybase * ta.pitch;
@@ -381,7 +422,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
 template <class C>
 SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = c.ps->nx;
+    const int nx = local_cols(c, c.ps->nx);
     const int nchunk = (nx + 31) >> 5;
     for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
         const int k1 = wi % C::E1, i = (wi / C::E1) * 32 + lane;
@@ -403,7 +444,7 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
 template <class C>
 SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = c.ps->nx;
+    const int nx = local_cols(c, c.ps->nx);
     const int nchunk = (nx + 31) >> 5;
     for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
         const int k1 = wi % C::E1, l = (wi / C::E1) * 32 + lane;
@@ -429,10 +470,11 @@ template <class C>
 SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
-    const int ny = ps.ny, nx = ps.nx;
+    const int ny = ps.ny, nx = local_cols(c, ps.nx);
     const int nchunk = (nx + 31) >> 5;
-    const int w2 = 2 * nx;
+    const int w2 = 2 * ps.nx;
     float *icc = c.icc;
+    const int cbase = 2 * c.col_lo;              // my columns start at surface column 2*col_lo
     Best best = best_init();
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, l = (wi / C::E2) * 32 + lane;
@@ -445,7 +487,7 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
         RegFFT<C::E1, true>::run(x);
         // sample n = E2*n1 + n2 is lag (n - shift) - yc -> surface row 2*(n-shift)+b
         const int nb = n2 - shift;
-        const int idx0 = (2 * nb + b) * w2 + 2 * l;
+        const int idx0 = (2 * nb + b) * w2 + 2 * l + cbase;
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         static_for<0, C::E1>([&](auto N1) {
@@ -473,9 +515,12 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
 template <class C, bool IS_REF>
 SPX_HD int row_of(const Ctx<C> &c, int chunk, int lane) {
     const int k = chunk * 32 + lane;
-    if (IS_REF) return k < C::RH ? int(c.rrow[k]) : -1;
+    if (IS_REF) return k < c.n_rrow ? int(c.rrow[k]) : -1;
+    if (C::CL == 2) return k < C::P / 2 ? int(c.xrow[k]) : -1;
     return k < C::P ? k : -1;
 }
+// row of the (local part of the) stored half spectrum that holds frequency row q
+template <class C> SPX_HD int rmap(int q) { return q / C::CL; }
 template <class C>
 SPX_HD cf *srow_of(const Ctx<C> &c, int r, int lane) {
     return C::INPLACE ? c.W + (r >= 0 ? r : 0) * C::WP : c.S + lane * C::SP;
@@ -491,9 +536,17 @@ SPX_HD void stage_in(const Ctx<C> &c, int tid, int chunk, int xoff) {
     for (int k = warp; k < 32; k += C::NW) {
         const int r = row_of<C, IS_REF>(c, chunk, k);
         if (r < 0) continue;
-        const cf *src = c.W + r * C::WP;
         cf *dst = c.S + k * C::SP + xoff;
-        for (int i = lane; i < nx; i += 32) dst[i] = src[i];
+        if (C::CL == 1) {
+            const cf *src = c.W + r * C::WP;
+            for (int i = lane; i < nx; i += 32) dst[i] = src[i];
+        } else {
+            // columns [0, NXL) live in rank 0's W, [NXL, 2*NXL) in rank 1's
+            const cf *w0 = (c.rank == 0 ? c.W : c.Wpeer) + r * C::WP;
+            const cf *w1 = (c.rank == 1 ? c.W : c.Wpeer) + r * C::WP;
+            for (int i = lane; i < nx; i += 32)
+                dst[i] = i < C::NXL ? w0[i] : w1[i - C::NXL];
+        }
     }
 }
 template <class C>
@@ -504,8 +557,17 @@ SPX_HD void stage_out(const Ctx<C> &c, int tid, int chunk, int shift) {
         const int r = row_of<C, false>(c, chunk, k);
         if (r < 0) continue;
         const cf *src = c.S + k * C::SP + shift;
-        cf *dst = c.W + r * C::WP;
-        for (int l = lane; l < nx; l += 32) dst[l] = src[l];
+        if (C::CL == 1) {
+            cf *dst = c.W + r * C::WP;
+            for (int l = lane; l < nx; l += 32) dst[l] = src[l];
+        } else {
+            cf *w0 = (c.rank == 0 ? c.W : c.Wpeer) + r * C::WP;
+            cf *w1 = (c.rank == 1 ? c.W : c.Wpeer) + r * C::WP;
+            for (int l = lane; l < nx; l += 32) {
+                if (l < C::NXL) w0[l] = src[l];
+                else w1[l - C::NXL] = src[l];
+            }
+        }
     }
 }
 
@@ -565,7 +627,7 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         });
         RegFFT<C::E2, false>::run(x);
         if (r >= 0) {
-            cf *Rrow = c.R + ky_of_row<C>(r) * C::RP + k1 * C::E2;
+            cf *Rrow = c.R + rmap<C>(ky_of_row<C>(r)) * C::RP + k1 * C::E2;
             static_for<0, C::E2>([&](auto K2) {
                 constexpr int k2 = decltype(K2)::value;
                 Rrow[k2] = cmake(x[k2].x * sc, -x[k2].y * sc);
@@ -585,7 +647,7 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         cf *srow = srow_of<C>(c, r, lane);
         const int ky = r >= 0 ? ky_of_row<C>(r) : 0;
         const bool flip = ky > C::P / 2;
-        const cf *Rrow = c.R + (flip ? C::P - ky : ky) * C::RP;
+        const cf *Rrow = c.R + rmap<C>(flip ? C::P - ky : ky) * C::RP;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
@@ -797,6 +859,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
         if (fl) ex.or_status(&ps->status, fl);
     });
     ex.par([&](int tid) { c2_pass<C>(c, tid, 0); });
+    if (C::CL == 2) ex.cluster_sync();           // both halves of W are complete
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, 0, C::RCHUNK, 0); });
         ex.par([&](int tid) { x2_ref_pass<C>(c, tid, 0, C::RCHUNK); });
@@ -807,6 +870,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
             ex.par([&](int tid) { x2_ref_pass<C>(c, tid, b, b + 1); });
         }
     }
+    if (C::CL == 2) ex.cluster_sync();           // the peer has read my W: it may be reused
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
@@ -815,6 +879,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
             if (fl) ex.or_status(&ps->status, fl);
         });
         ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
+        if (C::CL == 2) ex.cluster_sync();       // both halves of W are complete
         if (C::INPLACE) {
             ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
             ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
@@ -828,6 +893,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
                 ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
             }
         }
+        if (C::CL == 2) ex.cluster_sync();       // every row of W holds its lags again
         ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });
         ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh, cout); });
     }
@@ -842,6 +908,8 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 //   reduce_best_into(dst, f)  block argmax of f(tid) merged into *dst, barrier
 //   warp_fit(lane_f, final_f) one warp: sum lane_f(lane) over 32 lanes, then
 //                   final_f(sum) on one lane, then barrier
+//   cluster_sync()  barrier over both CTAs of a cluster (CL == 2 only)
+//   global_fence()  make this thread block's global writes visible to the peer
 //   or_status(p,v)  atomic OR
 // The device executor is in spx_cc.cu; tools/host_emu.cu runs the same
 // sequence serially on the CPU for debugging.
@@ -854,8 +922,28 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
 
     // ---- normalisation statistics (cc.py:131-156) ----------------------
     if (job.cc_type != SPX_CC) {
-        StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(*ps, tid); });
-        ex.single([&]() { stats_finalize(*ps, tot); });
+        StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(c, tid); });
+        if (C::CL == 2) {
+            // each CTA scanned its half of the columns: exchange and add in a fixed
+            // order so that both CTAs derive bit-identical statistics
+            ex.single([&]() {
+                const double v[8] = {tot.cnt, tot.sum, tot.sq, tot.rcnt, tot.rsum, tot.rsq,
+                                     double(tot.flags), 0.0};
+                for (int k = 0; k < 8; ++k) { c.xl->stat[c.rank][k] = v[k]; c.xp->stat[c.rank][k] = v[k]; }
+            });
+            ex.cluster_sync();
+            ex.single([&]() {
+                StatPartial t = stat_zero();
+                for (int rk = 0; rk < 2; ++rk) {
+                    const double *v = c.xl->stat[rk];
+                    t.cnt += v[0]; t.sum += v[1]; t.sq += v[2];
+                    t.rcnt += v[3]; t.rsum += v[4]; t.rsq += v[5]; t.flags |= int(v[6]);
+                }
+                stats_finalize(*ps, t);
+            });
+        } else {
+            ex.single([&]() { stats_finalize(*ps, tot); });
+        }
     }
 
     const bool fast = job.ny == C::NMAX && job.nx == C::NMAX && job.x1 >= 0 && job.y1 >= 0 &&
@@ -872,7 +960,22 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     }
 
     // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
-    {
+    if (C::CL == 2) {
+        // hand my best sample and my status bits to rank 0 (and vice versa)
+        ex.single([&]() {
+            c.xl->bestv[c.rank] = ps->best.v; c.xp->bestv[c.rank] = ps->best.v;
+            c.xl->besti[c.rank] = ps->best.idx; c.xp->besti[c.rank] = ps->best.idx;
+            c.xl->status[c.rank] = ps->status; c.xp->status[c.rank] = ps->status;
+        });
+        ex.global_fence();                       // my part of the surface is visible to rank 0
+        ex.cluster_sync();
+        ex.single([&]() {
+            Best o; o.v = c.xl->bestv[c.rank ^ 1]; o.idx = c.xl->besti[c.rank ^ 1];
+            if (best_better(o, ps->best)) ps->best = o;
+            ps->status |= c.xl->status[c.rank ^ 1];
+        });
+    }
+    if (C::CL == 1 || c.rank == 0) {
         const float *icc = c.icc;
         ex.warp_fit(
             [&](int lane) {
@@ -887,7 +990,7 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
                 ps->status = st;
             });
     }
-    if (job.patch_icc) {
+    if (job.patch_icc && (C::CL == 1 || c.rank == 0)) {
         ex.par([&](int tid) {
             const int st = ps->status;
             const int nanbits = SPX_S_NONFINITE_REF | SPX_S_BAD_NORM | SPX_S_NONFINITE_P00 |
@@ -902,12 +1005,27 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     }
 }
 
-// rows of W (scrambled ky order) whose frequency lies in the stored half
+// rows of W (scrambled ky order) whose frequency lies in the stored half (and,
+// in cluster mode, has my parity); returns their number
 template <class C>
-SPX_HD void build_rrow(uint16_t *rrow) {
+SPX_HD int build_rrow(uint16_t *rrow, int rank) {
     int k = 0;
-    for (int r = 0; r < C::P; ++r)
-        if (ky_of_row<C>(r) <= C::P / 2) rrow[k++] = uint16_t(r);
+    for (int r = 0; r < C::P; ++r) {
+        const int ky = ky_of_row<C>(r);
+        if (ky <= C::P / 2 && (C::CL == 1 || (ky & 1) == rank)) rrow[k++] = uint16_t(r);
+    }
+    return k;
+}
+// cluster mode: the rows whose row stage is mine - q(r) = min(ky, P - ky) has my
+// parity, so the R rows they need (q, direct or mirrored) are the ones I hold
+template <class C>
+SPX_HD int build_xrow(uint16_t *xrow, int rank) {
+    int k = 0;
+    for (int r = 0; r < C::P; ++r) {
+        const int ky = ky_of_row<C>(r), q = ky <= C::P / 2 ? ky : C::P - ky;
+        if ((q & 1) == rank) xrow[k++] = uint16_t(r);
+    }
+    return k;
 }
 
 }  // namespace spx

@@ -5,8 +5,10 @@
 //   /tmp/host_emu in.bin out.bin
 // in.bin : int32 n, ny, nx, cc_type, want_frames(0) ; float32 [n,5,ny,nx]
 // out.bin: float64 [n,2] shifts ; int32 [n] peak ; int32 [n] status ; float32 [n,2ny,2nx]
+#include <pthread.h>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 #include "../subpixal_b200/csrc/spx_cc_engine.cuh"
 
@@ -37,6 +39,9 @@ struct HostExec {
         for (int l = 0; l < 32; ++l) { FitSums f = lane_f(l); fit_add(tot, f); }
         final_f(tot);
     }
+    pthread_barrier_t *bar = nullptr;          // cluster barrier (two host threads = two CTAs)
+    void cluster_sync() { pthread_barrier_wait(bar); }
+    void global_fence() {}
     void or_status(int *p, int v) { *p |= v; }
     float load_icc(const float *p) { return *p; }
 };
@@ -44,23 +49,51 @@ struct HostExec {
 template <class C>
 void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts, int *peak,
          int *status, float *icc) {
-    std::vector<cf> W(C::W_ELEMS), S(C::S_ELEMS + 1), R(C::R_ELEMS);
-    std::vector<uint16_t> rrow(C::RH);
-    build_rrow<C>(rrow.data());
-    PairState ps;
-    Ctx<C> c;
-    c.W = W.data(); c.S = S.data(); c.R = R.data(); c.rrow = rrow.data(); c.ps = &ps;
-    HostExec<C> ex;
-    const size_t tile = size_t(ny) * nx;
-    for (int p = 0; p < n; ++p) {
-        c.icc = icc + size_t(p) * 4 * tile;
-        PairJob job;
-        for (int s = 0; s < 5; ++s) job.base[s] = stack + (size_t(p) * 5 + s) * tile;
-        job.pitch = nx; job.H = ny; job.W = nx; job.x1 = 0; job.y1 = 0;
-        job.ny = ny; job.nx = nx; job.cc_type = cc_type; job.status0 = 0;
-        job.flags = 0; job.patch_icc = true;
-        process_pair<C>(c, ex, job, shifts + 2 * p, peak + p, status + p);
+    constexpr int CL = C::CL;
+    std::vector<cf> W[2], S[2], R[2];
+    std::vector<uint16_t> rrow[2], xrow[2];
+    PairState ps[2];
+    Xchg xc[2];
+    Ctx<C> c[2];
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, CL);
+    for (int rk = 0; rk < CL; ++rk) {
+        W[rk].resize(C::W_ELEMS); S[rk].resize(C::S_ELEMS + 1); R[rk].resize(C::R_ELEMS);
+        rrow[rk].resize(C::RH); xrow[rk].resize(C::P);
+        c[rk].W = W[rk].data(); c[rk].S = S[rk].data(); c[rk].R = R[rk].data();
+        c[rk].rrow = rrow[rk].data(); c[rk].ps = &ps[rk];
+        c[rk].n_rrow = build_rrow<C>(rrow[rk].data(), rk);
+        c[rk].xrow = nullptr;
+        if (CL == 2) { build_xrow<C>(xrow[rk].data(), rk); c[rk].xrow = xrow[rk].data(); }
+        c[rk].rank = rk; c[rk].col_lo = rk * C::NXL;
+        c[rk].xl = &xc[rk];
     }
+    for (int rk = 0; rk < CL; ++rk) {
+        c[rk].Wpeer = CL == 2 ? W[rk ^ 1].data() : nullptr;
+        c[rk].xp = CL == 2 ? &xc[rk ^ 1] : nullptr;
+    }
+    const size_t tile = size_t(ny) * nx;
+    auto body = [&](int rk) {
+        HostExec<C> ex;
+        ex.bar = &bar;
+        for (int p = 0; p < n; ++p) {
+            c[rk].icc = icc + size_t(p) * 4 * tile;
+            PairJob job;
+            for (int s = 0; s < 5; ++s) job.base[s] = stack + (size_t(p) * 5 + s) * tile;
+            job.pitch = nx; job.H = ny; job.W = nx; job.x1 = 0; job.y1 = 0;
+            job.ny = ny; job.nx = nx; job.cc_type = cc_type; job.status0 = 0;
+            job.flags = 0; job.patch_icc = true;
+            process_pair<C>(c[rk], ex, job, shifts + 2 * p, peak + p, status + p);
+        }
+    };
+    if (CL == 1) {
+        body(0);
+    } else {
+        std::thread t1(body, 1);
+        body(0);
+        t1.join();
+    }
+    pthread_barrier_destroy(&bar);
 }
 
 int main(int argc, char **argv) {
@@ -78,7 +111,7 @@ int main(int argc, char **argv) {
     const int m = ny > nx ? ny : nx;
     if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
-    else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, false, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, true, true, false, 2>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else run<CcCfg<384, 24, 16, 256, 256, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     f = fopen(argv[2], "wb");
     fwrite(shifts.data(), 8, shifts.size(), f);

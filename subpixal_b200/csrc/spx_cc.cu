@@ -56,7 +56,10 @@ using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, tru
 #define SPX128_CLUSTER 1
 #endif
 #if SPX128_CLUSTER
-using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, true,  true,  false, 2>;   // 2-CTA cluster, DSMEM
+#ifndef SPX128_T
+#define SPX128_T 512
+#endif
+using Cfg128 = CcCfg<192, 12, 16, 128, SPX128_T, 1, true,  true,  false, 2>;   // 2-CTA cluster, DSMEM
 #else
 using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
 #endif

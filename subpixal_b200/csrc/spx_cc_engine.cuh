@@ -967,7 +967,8 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
             c.xl->besti[c.rank] = ps->best.idx; c.xp->besti[c.rank] = ps->best.idx;
             c.xl->status[c.rank] = ps->status; c.xp->status[c.rank] = ps->status;
         });
-        ex.global_fence();                       // my part of the surface is visible to rank 0
+        // the cluster barrier is a release/acquire fence at cluster scope: my part of
+        // the surface (global memory) is visible to rank 0 after it
         ex.cluster_sync();
         ex.single([&]() {
             Best o; o.v = c.xl->bestv[c.rank ^ 1]; o.idx = c.xl->besti[c.rank ^ 1];

@@ -13,7 +13,6 @@
 namespace spx {
 
 constexpr int kGatherThreads = 256;
-constexpr int kGatherRows = 32;        // rows of one cutout handled by a CTA
 
 struct GatherDev {
     const void *frame; const void *dq; const void *weight; const void *seg;
@@ -58,24 +57,30 @@ template <> __device__ __forceinline__ bool is_finite<double>(double v) {
 
 // Each warp owns kRowsPerWarp rows of the cutout and walks them together, so a
 // lane has kRowsPerWarp independent global loads in flight per step (the kernel
-// is latency bound otherwise: one 128-byte request per warp is ~1/4 of what
-// Little's law needs to saturate HBM).
-constexpr int kRowsPerWarp = kGatherRows / (kGatherThreads / 32);     // 4
+// is latency bound otherwise: one 128-byte request per warp is a fraction of
+// what Little's law needs to saturate HBM).  AUX = dq / segmentation / weight
+// planes present (their loads are batched with the pixel loads).
+#ifndef SPX_GATHER_RPW
+#define SPX_GATHER_RPW 4
+#endif
+constexpr int kRowsPerWarp = SPX_GATHER_RPW;
+constexpr int kGatherRowsPerCta = kRowsPerWarp * (kGatherThreads / 32);
 
-template <class T>
+template <class T, bool AUX>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev a) {
     const int k = blockIdx.y;
     const int4 box = __ldg(reinterpret_cast<const int4 *>(a.boxes) + k);
     const int x1 = box.x, y1 = box.y, w = box.z - box.x + 1, h = box.w - box.y + 1;
-    const int row0 = blockIdx.x * kGatherRows;
+    const int row0 = blockIdx.x * kGatherRowsPerCta;
     if (row0 >= h || w <= 0) return;
     const long long off = a.out_offset[k];
-    const long long sid = a.src_ids ? a.src_ids[k] : 0;
+    const long long sid = (AUX && a.src_ids) ? a.src_ids[k] : 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const T *frame = static_cast<const T *>(a.frame);
     T *out = static_cast<T *>(a.data_out);
     const T fill = T(a.fillval);
-    const bool aux = a.dq || (a.seg && a.src_ids) || (a.weight && a.weight_out);
+    const bool want_dq = AUX && a.dq != nullptr, want_seg = AUX && a.seg && a.src_ids;
+    const bool want_w = AUX && a.weight && a.weight_out;
     const int rbase = row0 + warp * kRowsPerWarp;
     for (int col = lane; col < w; col += 32) {
         const int xx = x1 + col;
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev 
         T v[kRowsPerWarp];
         bool inside[kRowsPerWarp];
 #pragma unroll
-        for (int r = 0; r < kRowsPerWarp; ++r) {                       // loads first
+        for (int r = 0; r < kRowsPerWarp; ++r) {                       // pixel loads first
             const int row = rbase + r, yy = y1 + row;
             inside[r] = incol && row < h && yy >= 0 && yy < a.H;      // cutout.py:742-752
             v[r] = inside[r] ? __ldg(frame + (long long)yy * a.frame_pitch + xx) : fill;
@@ -95,18 +100,18 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev 
             const long long o = off + (long long)row * w + col;
             T val = v[r];
             bool bad = !inside[r] || !is_finite<T>(val);               // cutout.py:755
-            if (aux) {
+            if (AUX) {
                 const long long src = (long long)(y1 + row) * a.W + xx;
-                if (a.dq) {                                            // cutout.py:758-766
+                if (want_dq) {                                         // cutout.py:758-766
                     const long long d = inside[r] ? load_bits(a.dq, src, a.dq_bytes) : 0;
                     if (a.dq_out) store_int(a.dq_out, o, a.dq_bytes, d);
                     if (a.dq_use_bits) bad |= (d & ~a.dq_good_bits) != 0;   // cutout.py:190-193
                 }
-                if (a.seg && a.src_ids) {                              // cutout.py:188, 416-419
+                if (want_seg) {                                        // cutout.py:188, 416-419
                     const long long sg = inside[r] ? load_int(a.seg, src, a.seg_bytes) : 0;
                     bad |= (sg != sid);
                 }
-                if (a.weight && a.weight_out) {                        // cutout.py:769-779
+                if (want_w) {                                          // cutout.py:769-779
                     if (a.weight_f64)
                         static_cast<double *>(a.weight_out)[o] =
                             inside[r] ? static_cast<const double *>(a.weight)[src] : 0.0;
@@ -154,7 +159,8 @@ extern "C" int spx_gather_cutouts(const spx_gather_args *g, void *stream) {
     }
     if (g->n == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int rows = (g->max_h + kGatherRows - 1) / kGatherRows;
+    const int rows = (g->max_h + kGatherRowsPerCta - 1) / kGatherRowsPerCta;
+    const bool aux = g->dq || (g->seg && g->src_ids) || (g->weight && g->weight_out);
     for (int k0 = 0; k0 < g->n; k0 += 65535) {              // gridDim.y limit
         const int nk = (g->n - k0 < 65535) ? g->n - k0 : 65535;
         GatherDev b = a;
@@ -162,8 +168,13 @@ extern "C" int spx_gather_cutouts(const spx_gather_args *g, void *stream) {
         b.out_offset = a.out_offset + k0;
         if (a.src_ids) b.src_ids = a.src_ids + k0;
         dim3 grid(rows, nk);
-        if (g->frame_kind == SPX_T_F32) gather_kernel<float><<<grid, kGatherThreads, 0, st>>>(b);
-        else gather_kernel<double><<<grid, kGatherThreads, 0, st>>>(b);
+        if (g->frame_kind == SPX_T_F32) {
+            if (aux) gather_kernel<float, true><<<grid, kGatherThreads, 0, st>>>(b);
+            else gather_kernel<float, false><<<grid, kGatherThreads, 0, st>>>(b);
+        } else {
+            if (aux) gather_kernel<double, true><<<grid, kGatherThreads, 0, st>>>(b);
+            else gather_kernel<double, false><<<grid, kGatherThreads, 0, st>>>(b);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return int(e);
     }

@@ -28,7 +28,7 @@ __device__ __forceinline__ double py2round_dev(double x) {        // utils.py:14
 }
 
 template <class T>
-__global__ void __launch_bounds__(kPeakThreads) find_peak_kernel(const PeakParams p) {
+__global__ void __launch_bounds__(kPeakThreads, 4) find_peak_kernel(const PeakParams p) {
     __shared__ double s_v[kPeakThreads / 32];
     __shared__ int s_i[kPeakThreads / 32];
     const int k = blockIdx.x;
@@ -58,7 +58,25 @@ __global__ void __launch_bounds__(kPeakThreads) find_peak_kernel(const PeakParam
     bool found = false;
     if (search) {
         const int bw = sx2 - sx1, cnt = bw * (sy2 - sy1);
-        if (bw == p.w) {
+        if (bw == p.w && sizeof(T) == 4 && !use_mask && (cnt & 3) == 0 &&
+            (reinterpret_cast<size_t>(img + sy1 * p.w) & 15) == 0) {
+            // contiguous float32 samples, 16-byte aligned: 128-bit loads, two in flight
+            const int base = sy1 * p.w;
+            const float4 *v4 = reinterpret_cast<const float4 *>(img + base);
+            const int n4 = cnt >> 2;
+            for (int t0 = tid; t0 < n4; t0 += 2 * kPeakThreads) {
+                const int t1 = t0 + kPeakThreads;
+                const float4 a = __ldg(v4 + t0);
+                const float4 b = t1 < n4 ? __ldg(v4 + t1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float va[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (u >= 4 && t1 >= n4) break;
+                    BestD c; c.v = double(va[u]); c.idx = base + 4 * (u < 4 ? t0 : t1) + (u & 3);
+                    if (!found || bestd_better(c, best)) { best = c; found = true; }
+                }
+            }
+        } else if (bw == p.w) {
             // full-width window: the samples are contiguous, no div/mod, four
             // independent loads in flight per thread
             const int base = sy1 * p.w;

@@ -74,7 +74,7 @@ template <class C> struct Layout {
     static constexpr size_t off_rrow = off_xchg + 256;
     static constexpr size_t rrow_bytes = ((C::RH * 2 + 15) / 16) * 16;
     static constexpr size_t off_xrow = off_rrow + rrow_bytes;
-    static constexpr size_t xrow_bytes = C::CL == 2 ? ((C::P + 15) / 16) * 16 : 0;
+    static constexpr size_t xrow_bytes = 0;
     static constexpr size_t off_S = off_xrow + xrow_bytes;
     static constexpr size_t off_W = off_S + C::S_ELEMS * 8;
     static constexpr size_t off_R = off_W + (C::W_SMEM ? C::W_ELEMS * 8 : 0);
@@ -208,7 +208,6 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     extern __shared__ __align__(16) unsigned char smem[];
     using L = Layout<C>;
     uint16_t *rrow = reinterpret_cast<uint16_t *>(smem + L::off_rrow);
-    uint16_t *xrow = reinterpret_cast<uint16_t *>(smem + L::off_xrow);
     // one pair per CTA, or per cluster of CL CTAs
     const int rank = C::CL == 2 ? int(cg::this_cluster().block_rank()) : 0;
     const int unit = blockIdx.x / C::CL, nunits = gridDim.x / C::CL;
@@ -221,7 +220,6 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     c.R = C::R_SMEM ? reinterpret_cast<cf *>(smem + L::off_R)
                     : reinterpret_cast<cf *>(slab + prm.off_r);
     c.rrow = rrow;
-    c.xrow = C::CL == 2 ? xrow : nullptr;
     c.ps = reinterpret_cast<PairState *>(smem + L::off_ps);
     c.rank = rank;
     c.col_lo = rank * C::NXL;
@@ -239,7 +237,6 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     __shared__ int s_nrrow;
     if (threadIdx.x == 0) {
         s_nrrow = build_rrow<C>(rrow, rank);
-        if (C::CL == 2) build_xrow<C>(xrow, rank);
     }
     __syncthreads();
     c.n_rrow = s_nrrow;

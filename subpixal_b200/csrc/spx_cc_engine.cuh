@@ -65,12 +65,13 @@ SPX_TW(48) SPX_TW(96) SPX_TW(192) SPX_TW(384)
 // (used when W lives in global memory).
 //
 // CL = 2: one pair is processed by a thread-block cluster of two CTAs.  W is
-// split by COLUMNS (each CTA holds all P rows of NMAX/2 columns in its shared
-// memory, so the column passes are purely local); the row stage of row r is done
-// by the CTA that owns r, which pulls the other half of the row out of the peer's
-// shared memory (DSMEM) and pushes the results back.  Rows are assigned by the
-// parity of q(r) = min(ky, P-ky), so that each CTA only needs the R rows of its
-// own parity (half of R).
+// split by ROWS: the rows r = k1*E2 + k2 of one k1 group all have ky = k1 + E1*k2
+// of the same parity as k1 (E1 even), hence the same parity of q = min(ky, P-ky).
+// CTA `rank` owns the groups with k1 % 2 == rank: C2, the whole row stage and IC1
+// are then purely local and need only the R rows of parity `rank` (half of R).
+// Only C1 (stores half of its outputs into the peer's shared memory) and IC2
+// (loads half of its inputs from it) cross the cluster, through DSMEM; the tile
+// columns, and therefore all HBM traffic, are split half / half.
 template <int P_, int E1_, int E2_, int NMAX_, int T_, int MINB_, bool WSM_, bool RSM_,
           bool INPLACE_ = false, int CL_ = 1>
 struct CcCfg {
@@ -78,19 +79,24 @@ struct CcCfg {
     static constexpr bool W_SMEM = WSM_, R_SMEM = RSM_, INPLACE = INPLACE_;
     static constexpr int CL = CL_;
     static constexpr int NW = T / 32;
-    static constexpr int NXL = NMAX / CL;    // columns of W held by one CTA
-    static constexpr int WP = INPLACE ? P + 1 : NXL + 1;    // pitch of W (complex), odd
+    static constexpr int NXL = NMAX / CL;    // tile columns loaded / finished by one CTA
+    static constexpr int E1L = E1 / CL;      // k1 groups (of E2 rows each) held by one CTA
+    static constexpr int PL = P / CL;        // rows of W held by one CTA
+    static constexpr int WP = INPLACE ? P + 1 : NMAX + 1;   // pitch of W (complex), odd
+    // how the row stage reaches its rows: in place in W / directly in W (shared
+    // memory, lanes along rows) / staged through S by coalesced copies (W global)
+    static constexpr bool DIRECT = !INPLACE && WSM_;
     static constexpr int SP = P + 1;         // pitch of the row scratch, odd
     static constexpr int RP = P + 1;         // pitch of R, odd
     static constexpr int RH = P / 2 + 1;     // rows of R (half spectrum)
     static constexpr int RHL = (RH + CL - 1) / CL;   // ... held by one CTA
     static constexpr int BATCH = 32;         // rows per row-op batch (= lanes)
-    static constexpr int NCHUNK = (P / CL + 31) / 32, RCHUNK = (RHL + 31) / 32;
-    static constexpr size_t W_ELEMS = size_t(P) * WP;
+    static constexpr int NCHUNK = (PL + 31) / 32, RCHUNK = (RHL + 31) / 32;
+    static constexpr size_t W_ELEMS = size_t(PL) * WP;
     static constexpr size_t S_ELEMS = INPLACE ? 0 : size_t(BATCH) * SP;
     static constexpr size_t R_ELEMS = size_t(RHL) * RP;
-    static_assert(CL == 1 || (CL == 2 && !INPLACE && WSM_ && RSM_ && P % 64 == 0),
-                  "cluster mode: staged row stage, W and R in shared memory");
+    static_assert(CL == 1 || (CL == 2 && !INPLACE && WSM_ && RSM_ && E1 % 2 == 0),
+                  "cluster mode: W and R in shared memory, even E1");
     static_assert(E1 * E2 == P, "P = E1*E2");
     static_assert(P % 2 == 0 && NMAX % 2 == 0, "even sizes");
     static_assert(T % 32 == 0, "whole warps");
@@ -129,12 +135,11 @@ template <class C>
 struct Ctx {
     cf *W, *S, *R;
     float *icc;            // [2ny][2nx] interlaced surface of this pair
-    const uint16_t *rrow;  // rows of W (scrambled ky order) with ky <= P/2 (of my parity)
+    const uint16_t *rrow;  // my rows of W (local index) with ky <= P/2
     PairState *ps;
     // cluster mode (CL == 2); rank = 0, col_lo = 0 and null pointers otherwise
     int rank, col_lo, n_rrow;
     cf *Wpeer;             // the peer CTA's W (distributed shared memory)
-    const uint16_t *xrow;  // rows of W whose row stage is mine
     Xchg *xl, *xp;         // local / peer exchange block
 };
 
@@ -174,8 +179,15 @@ SPX_HD float ld_f32_last(const float *p) {
 #endif
 }
 
-// W row r holds frequency ky = r/E2 + E1*(r%E2)  (in-place two-step order)
-template <class C> SPX_HD int ky_of_row(int r) { return r / C::E2 + C::E1 * (r % C::E2); }
+// Row r = k1*E2 + k2 holds frequency ky = k1 + E1*k2 (in-place two-step order).
+// Cluster mode: CTA `rank` stores the groups k1 = 2j + rank at local rows j*E2 + k2.
+template <class C> SPX_HD int ky_of_row(int lr, int rank) {
+    return (lr / C::E2) * C::CL + rank + C::E1 * (lr % C::E2);
+}
+// base pointer and local row of W row (k1, k2) as seen from CTA `c.rank`
+template <class C, int K1> SPX_HD cf *w_of_k1(cf *mine, cf *peer, int rank) {
+    return (C::CL == 1 || (K1 % C::CL) == rank) ? mine : peer;
+}
 
 SPX_HD unsigned f32_bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
 
@@ -409,33 +421,35 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
         }
         RegFFT<C::E1, false>::run(x);
         if (active) {
+            const int gi = c.col_lo + i + col0;              // column inside W
             static_for<0, C::E1>([&](auto K1) {
                 constexpr int k1 = decltype(K1)::value;
-                c.W[(k1 * C::E2 + n2) * C::WP + i + col0] = cmul(x[k1], tw<C::P>(n2 * k1));
+                cf *wb = w_of_k1<C, k1>(c.W, c.Wpeer, c.rank);   // owner of the k1 group
+                wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gi] = cmul(x[k1], tw<C::P>(n2 * k1));
             });
         }
     }
     return flags;
 }
 
-// C2: E2-point FFT over n2 for every (column, k1), in place.
+// C2: E2-point FFT over n2 for every (column, k1 group of mine), in place.
 template <class C>
 SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = local_cols(c, c.ps->nx);
+    const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
-    for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
-        const int k1 = wi % C::E1, i = (wi / C::E1) * 32 + lane;
+    for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
+        const int j = wi % C::E1L, i = (wi / C::E1L) * 32 + lane;
         if (i >= nx) continue;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            x[n2] = c.W[(k1 * C::E2 + n2) * C::WP + i + col0];
+            x[n2] = c.W[(j * C::E2 + n2) * C::WP + i + col0];
         });
         RegFFT<C::E2, false>::run(x);
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            c.W[(k1 * C::E2 + k2) * C::WP + i + col0] = x[k2];
+            c.W[(j * C::E2 + k2) * C::WP + i + col0] = x[k2];
         });
     }
 }
@@ -444,20 +458,21 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
 template <class C>
 SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = local_cols(c, c.ps->nx);
+    const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
-    for (int wi = warp; wi < nchunk * C::E1; wi += C::NW) {
-        const int k1 = wi % C::E1, l = (wi / C::E1) * 32 + lane;
+    for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
+        const int j = wi % C::E1L, l = (wi / C::E1L) * 32 + lane;
+        const int k1 = j * C::CL + c.rank;
         if (l >= nx) continue;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            x[k2] = c.W[(k1 * C::E2 + k2) * C::WP + l + col0];
+            x[k2] = c.W[(j * C::E2 + k2) * C::WP + l + col0];
         });
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            c.W[(k1 * C::E2 + n2) * C::WP + l + col0] = cmulc(x[n2], tw<C::P>(n2 * k1));
+            c.W[(j * C::E2 + n2) * C::WP + l + col0] = cmulc(x[n2], tw<C::P>(n2 * k1));
         });
     }
 }
@@ -480,9 +495,11 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
         const int n2 = wi % C::E2, l = (wi / C::E2) * 32 + lane;
         if (l >= nx) continue;
         cf x[C::E1];
+        const int gl = c.col_lo + l + col0;                 // column inside W
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
-            x[k1] = c.W[(k1 * C::E2 + n2) * C::WP + l + col0];
+            const cf *wb = w_of_k1<C, k1>(c.W, c.Wpeer, c.rank);
+            x[k1] = wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gl];
         });
         RegFFT<C::E1, true>::run(x);
         // sample n = E2*n1 + n2 is lag (n - shift) - yc -> surface row 2*(n-shift)+b
@@ -516,8 +533,7 @@ template <class C, bool IS_REF>
 SPX_HD int row_of(const Ctx<C> &c, int chunk, int lane) {
     const int k = chunk * 32 + lane;
     if (IS_REF) return k < c.n_rrow ? int(c.rrow[k]) : -1;
-    if (C::CL == 2) return k < C::P / 2 ? int(c.xrow[k]) : -1;
-    return k < C::P ? k : -1;
+    return k < C::PL ? k : -1;
 }
 // row of the (local part of the) stored half spectrum that holds frequency row q
 template <class C> SPX_HD int rmap(int q) { return q / C::CL; }
@@ -536,17 +552,9 @@ SPX_HD void stage_in(const Ctx<C> &c, int tid, int chunk, int xoff) {
     for (int k = warp; k < 32; k += C::NW) {
         const int r = row_of<C, IS_REF>(c, chunk, k);
         if (r < 0) continue;
+        const cf *src = c.W + r * C::WP;
         cf *dst = c.S + k * C::SP + xoff;
-        if (C::CL == 1) {
-            const cf *src = c.W + r * C::WP;
-            for (int i = lane; i < nx; i += 32) dst[i] = src[i];
-        } else {
-            // columns [0, NXL) live in rank 0's W, [NXL, 2*NXL) in rank 1's
-            const cf *w0 = (c.rank == 0 ? c.W : c.Wpeer) + r * C::WP;
-            const cf *w1 = (c.rank == 1 ? c.W : c.Wpeer) + r * C::WP;
-            for (int i = lane; i < nx; i += 32)
-                dst[i] = i < C::NXL ? w0[i] : w1[i - C::NXL];
-        }
+        for (int i = lane; i < nx; i += 32) dst[i] = src[i];
     }
 }
 template <class C>
@@ -557,17 +565,8 @@ SPX_HD void stage_out(const Ctx<C> &c, int tid, int chunk, int shift) {
         const int r = row_of<C, false>(c, chunk, k);
         if (r < 0) continue;
         const cf *src = c.S + k * C::SP + shift;
-        if (C::CL == 1) {
-            cf *dst = c.W + r * C::WP;
-            for (int l = lane; l < nx; l += 32) dst[l] = src[l];
-        } else {
-            cf *w0 = (c.rank == 0 ? c.W : c.Wpeer) + r * C::WP;
-            cf *w1 = (c.rank == 1 ? c.W : c.Wpeer) + r * C::WP;
-            for (int l = lane; l < nx; l += 32) {
-                if (l < C::NXL) w0[l] = src[l];
-                else w1[l - C::NXL] = src[l];
-            }
-        }
+        cf *dst = c.W + r * C::WP;
+        for (int l = lane; l < nx; l += 32) dst[l] = src[l];
     }
 }
 
@@ -583,10 +582,10 @@ SPX_HD void x1_pass(const Ctx<C> &c, int tid, int cb, int ce, int xoff) {
         const int chunk = wi / C::E2, n2 = wi - chunk * C::E2;
         const int r = row_of<C, IS_REF>(c, chunk, lane);
         if (C::INPLACE && r < 0) continue;
-        // the row buffer (W row itself, or the staged copy in S) is indexed by
-        // padded position
+        // the P-wide row buffer (the W row itself / a row of S) is indexed by padded
+        // position; DIRECT mode reads the nx input samples straight from the W row
         cf *srow = srow_of<C>(c, r, lane);
-        const cf *in = srow;
+        const cf *in = C::DIRECT ? c.W + (r >= 0 ? r : 0) * C::WP - xoff : srow;
         cf x[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
@@ -627,7 +626,7 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         });
         RegFFT<C::E2, false>::run(x);
         if (r >= 0) {
-            cf *Rrow = c.R + rmap<C>(ky_of_row<C>(r)) * C::RP + k1 * C::E2;
+            cf *Rrow = c.R + rmap<C>(ky_of_row<C>(r, c.rank)) * C::RP + k1 * C::E2;
             static_for<0, C::E2>([&](auto K2) {
                 constexpr int k2 = decltype(K2)::value;
                 Rrow[k2] = cmake(x[k2].x * sc, -x[k2].y * sc);
@@ -645,7 +644,7 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         const int r = row_of<C, false>(c, chunk, lane);
         if (C::INPLACE && r < 0) continue;
         cf *srow = srow_of<C>(c, r, lane);
-        const int ky = r >= 0 ? ky_of_row<C>(r) : 0;
+        const int ky = r >= 0 ? ky_of_row<C>(r, c.rank) : 0;
         const bool flip = ky > C::P / 2;
         const cf *Rrow = c.R + rmap<C>(flip ? C::P - ky : ky) * C::RP;
         cf x[C::E2];
@@ -692,7 +691,8 @@ SPX_HD void x3_pass(const Ctx<C> &c, int tid, int cb, int ce, int shift) {
         });
         RegFFT<C::E1, true>::run(x);
         if (r >= 0) {
-            cf *out = srow_of<C>(c, r, lane);
+            // DIRECT: lag sample l = m - shift goes to column l of the W row
+            cf *out = C::DIRECT ? c.W + r * C::WP - shift : srow_of<C>(c, r, lane);
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
                 const int m = C::E2 * n1 + n2;
@@ -858,19 +858,19 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
         const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0);
         if (fl) ex.or_status(&ps->status, fl);
     });
+    if (C::CL == 2) ex.cluster_sync();           // the peer's half of my rows has arrived
     ex.par([&](int tid) { c2_pass<C>(c, tid, 0); });
-    if (C::CL == 2) ex.cluster_sync();           // both halves of W are complete
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, 0, C::RCHUNK, 0); });
         ex.par([&](int tid) { x2_ref_pass<C>(c, tid, 0, C::RCHUNK); });
     } else {
         for (int b = 0; b < C::RCHUNK; ++b) {
-            ex.par([&](int tid) { stage_in<C, true>(c, tid, b, 0); });
+            if (!C::DIRECT) ex.par([&](int tid) { stage_in<C, true>(c, tid, b, 0); });
             ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, b, b + 1, 0); });
             ex.par([&](int tid) { x2_ref_pass<C>(c, tid, b, b + 1); });
         }
     }
-    if (C::CL == 2) ex.cluster_sync();           // the peer has read my W: it may be reused
+    if (C::CL == 2) ex.cluster_sync();           // I am done with W: the peer's next C1 may write it
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
@@ -878,24 +878,27 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
             const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin);
             if (fl) ex.or_status(&ps->status, fl);
         });
+        if (C::CL == 2) ex.cluster_sync();       // the peer's half of my rows has arrived
         ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
-        if (C::CL == 2) ex.cluster_sync();       // both halves of W are complete
         if (C::INPLACE) {
             ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
             ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
             ex.par([&](int tid) { x3_pass<C>(c, tid, 0, C::NCHUNK, xsh); });
         } else {
             for (int k = 0; k < C::NCHUNK; ++k) {
-                ex.par([&](int tid) { stage_in<C, false>(c, tid, k, xoff); });
+                if (!C::DIRECT) ex.par([&](int tid) { stage_in<C, false>(c, tid, k, xoff); });
                 ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff); });
                 ex.par([&](int tid) { x2_pass<C>(c, tid, k, k + 1); });
                 ex.par([&](int tid) { x3_pass<C>(c, tid, k, k + 1, xsh); });
-                ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
+                if (!C::DIRECT) ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
             }
         }
-        if (C::CL == 2) ex.cluster_sync();       // every row of W holds its lags again
         ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });
+        if (C::CL == 2) ex.cluster_sync();       // the peer's rows hold their lags: IC2 may read them
         ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh, cout); });
+        // the peer must not start writing my rows (its next C1) while I still read
+        // them; after the second pair the exchange barrier of the peak stage does that
+        if (C::CL == 2 && b == 0) ex.cluster_sync();
     }
 }
 
@@ -1006,26 +1009,13 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     }
 }
 
-// rows of W (scrambled ky order) whose frequency lies in the stored half (and,
-// in cluster mode, has my parity); returns their number
+// my rows of W (local index) whose frequency lies in the stored half ky <= P/2;
+// returns their number
 template <class C>
 SPX_HD int build_rrow(uint16_t *rrow, int rank) {
     int k = 0;
-    for (int r = 0; r < C::P; ++r) {
-        const int ky = ky_of_row<C>(r);
-        if (ky <= C::P / 2 && (C::CL == 1 || (ky & 1) == rank)) rrow[k++] = uint16_t(r);
-    }
-    return k;
-}
-// cluster mode: the rows whose row stage is mine - q(r) = min(ky, P - ky) has my
-// parity, so the R rows they need (q, direct or mirrored) are the ones I hold
-template <class C>
-SPX_HD int build_xrow(uint16_t *xrow, int rank) {
-    int k = 0;
-    for (int r = 0; r < C::P; ++r) {
-        const int ky = ky_of_row<C>(r), q = ky <= C::P / 2 ? ky : C::P - ky;
-        if ((q & 1) == rank) xrow[k++] = uint16_t(r);
-    }
+    for (int lr = 0; lr < C::PL; ++lr)
+        if (ky_of_row<C>(lr, rank) <= C::P / 2) rrow[k++] = uint16_t(lr);
     return k;
 }
 

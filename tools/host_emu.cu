@@ -51,7 +51,7 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
          int *status, float *icc) {
     constexpr int CL = C::CL;
     std::vector<cf> W[2], S[2], R[2];
-    std::vector<uint16_t> rrow[2], xrow[2];
+    std::vector<uint16_t> rrow[2];
     PairState ps[2];
     Xchg xc[2];
     Ctx<C> c[2];
@@ -59,12 +59,10 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
     pthread_barrier_init(&bar, nullptr, CL);
     for (int rk = 0; rk < CL; ++rk) {
         W[rk].resize(C::W_ELEMS); S[rk].resize(C::S_ELEMS + 1); R[rk].resize(C::R_ELEMS);
-        rrow[rk].resize(C::RH); xrow[rk].resize(C::P);
+        rrow[rk].resize(C::RH);
         c[rk].W = W[rk].data(); c[rk].S = S[rk].data(); c[rk].R = R[rk].data();
         c[rk].rrow = rrow[rk].data(); c[rk].ps = &ps[rk];
         c[rk].n_rrow = build_rrow<C>(rrow[rk].data(), rk);
-        c[rk].xrow = nullptr;
-        if (CL == 2) { build_xrow<C>(xrow[rk].data(), rk); c[rk].xrow = xrow[rk].data(); }
         c[rk].rank = rk; c[rk].col_lo = rk * C::NXL;
         c[rk].xl = &xc[rk];
     }

@@ -59,7 +59,10 @@ using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, tru
 #ifndef SPX128_T
 #define SPX128_T 512
 #endif
-using Cfg128 = CcCfg<192, 12, 16, 128, SPX128_T, 1, true,  true,  false, 2>;   // 2-CTA cluster, DSMEM
+#ifndef SPX128_INPLACE
+#define SPX128_INPLACE 1
+#endif
+using Cfg128 = CcCfg<192, 12, 16, 128, SPX128_T, 1, true,  true,  SPX128_INPLACE != 0, 2>;   // 2-CTA cluster, DSMEM
 #else
 using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
 #endif
@@ -181,25 +184,56 @@ struct DevExec {
 
 // Pull the five tiles of a (future) pair into L2 so that its loads do not pay
 // the HBM latency: one prefetch per 128-byte line, spread over the CTA.
+// The lane -> (row within a group, tile, line) mapping depends only on nx, so
+// it is computed once per kernel (PfMap) and the per-pair loop has no divisions.
+struct PfMap { int s, seg, rr, rpi; };      // s < 0: lane idle; rpi: rows per warp iteration
+__device__ __forceinline__ PfMap prefetch_map(int nx, int lane) {
+    PfMap m;
+    const int segs = (nx * 4 + 127) / 128 + 1;           // lines a row can touch (unaligned start)
+    const int per = 5 * segs;
+    m.rpi = per <= 32 ? 32 / per : 0;                    // 0: generic path (rows wider than 160 px)
+    m.rr = m.rpi ? lane / per : 0;
+    const int k = lane - m.rr * per;
+    m.s = k / segs; m.seg = k - m.s * segs;
+    if (m.rr >= m.rpi) m.s = -1;
+    return m;
+}
 template <class C>
-__device__ __forceinline__ void prefetch_pair(const CcParams &prm, int p) {
+__device__ __forceinline__ void prefetch_pair(const CcParams &prm, int p, const PfMap &m) {
     if (p >= prm.n) return;
     int x1 = 0, y1 = 0;
     if (prm.boxes) {
         const int4 b = __ldg(reinterpret_cast<const int4 *>(prm.boxes) + p);
         x1 = b.x; y1 = b.y;
     }
-    const int segs = (prm.nx + 31) / 32 + 1;             // 128-byte segments per row (unaligned start)
-    const int per_tile = prm.ny * segs;
-    for (int t = threadIdx.x; t < 5 * per_tile; t += C::T) {
-        const int s = t / per_tile, rem = t - s * per_tile;
-        const int row = rem / segs, seg = rem - row * segs;
-        const int yy = y1 + row;
-        int xx = x1 + seg * 32;
-        if (xx > x1 + prm.nx - 1) xx = x1 + prm.nx - 1;
-        if (yy < 0 || yy >= prm.H || xx < 0 || xx >= prm.W) continue;
-        const float *ptr = prm.src[s] + size_t(p) * prm.pair_stride[s] + (long long)yy * prm.pitch + xx;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    // columns / rows of the box that exist in the source image
+    const int xa = x1 < 0 ? 0 : x1, xb = x1 + prm.nx > prm.W ? prm.W : x1 + prm.nx;
+    const int ya = y1 < 0 ? 0 : y1, yb = y1 + prm.ny > prm.H ? prm.H : y1 + prm.ny;
+    if (xa >= xb || ya >= yb) return;
+    const int rows = yb - ya;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (m.rpi) {
+        if (m.s < 0) return;
+        const float *base = prm.src[m.s] + size_t(p) * prm.pair_stride[m.s] + (long long)ya * prm.pitch;
+        for (int r = warp * m.rpi + m.rr; r < rows; r += C::NW * m.rpi) {
+            const float *row = base + (long long)r * prm.pitch;
+            const uintptr_t line = (reinterpret_cast<uintptr_t>(row + xa) & ~uintptr_t(127)) + m.seg * 128;
+            if (line < reinterpret_cast<uintptr_t>(row + xb))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+        }
+    } else {
+        const int segs = (prm.nx * 4 + 127) / 128 + 1;
+        for (int s = 0; s < 5; ++s) {
+            const float *base = prm.src[s] + size_t(p) * prm.pair_stride[s] + (long long)ya * prm.pitch;
+            for (int r = warp; r < rows; r += C::NW) {
+                const float *row = base + (long long)r * prm.pitch;
+                for (int seg = lane; seg < segs; seg += 32) {
+                    const uintptr_t line = (reinterpret_cast<uintptr_t>(row + xa) & ~uintptr_t(127)) + seg * 128;
+                    if (line < reinterpret_cast<uintptr_t>(row + xb))
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+                }
+            }
+        }
     }
 }
 
@@ -243,6 +277,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     if (C::CL == 2) cg::this_cluster().sync();     // the peer is resident: DSMEM may be used
 
     const size_t icc_elems = size_t(4) * prm.ny * prm.nx;
+    const PfMap pfmap = prefetch_map(prm.nx, threadIdx.x & 31);
     for (int p = unit; p < prm.n; p += nunits) {
         c.icc = prm.icc_out ? prm.icc_out + size_t(p) * icc_elems
                             : reinterpret_cast<float *>(slab + prm.off_icc);
@@ -258,7 +293,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
         job.pitch = prm.pitch; job.H = prm.H; job.W = prm.W;
         job.ny = prm.ny; job.nx = prm.nx; job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
-        if (rank == 0) prefetch_pair<C>(prm, p + nunits);
+        if (rank == 0) prefetch_pair<C>(prm, p + nunits, pfmap);
         process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
     }
     if (C::CL == 2) cg::this_cluster().sync();     // do not exit while the peer may still read my W

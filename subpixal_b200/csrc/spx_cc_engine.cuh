@@ -36,25 +36,20 @@ namespace spx {
 // --------------------------------------------------------------------------
 // twiddle tables: __constant__ on the device, plain statics for the host emu
 // --------------------------------------------------------------------------
+// two-step twiddle W_P^(n2*k1) from the [n2][k1] table (one of the two indices is
+// a compile-time constant at every call site -> base register + immediate)
 #ifndef SPX_HOST_EMU
-__constant__ TwTable<48>  c_tw48  = TwTable<48>();
-__constant__ TwTable<96>  c_tw96  = TwTable<96>();
-__constant__ TwTable<192> c_tw192 = TwTable<192>();
-__constant__ TwTable<384> c_tw384 = TwTable<384>();
+template <int P, int E1> __constant__ TwTable2<P, E1> c_tw2 = TwTable2<P, E1>();
 #endif
-static const TwTable<48>  h_tw48  = TwTable<48>();
-static const TwTable<96>  h_tw96  = TwTable<96>();
-static const TwTable<192> h_tw192 = TwTable<192>();
-static const TwTable<384> h_tw384 = TwTable<384>();
-
-template <int P> SPX_HD cf tw(int k);
+template <int P, int E1> struct HostTw2 { static const TwTable2<P, E1> t; };
+template <int P, int E1> const TwTable2<P, E1> HostTw2<P, E1>::t = TwTable2<P, E1>();
+template <class C> SPX_HD cf tw2(int n2, int k1) {
 #if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
-#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return c_tw##P.w[k]; }
+    return c_tw2<C::P, C::E1>.w[n2 * C::E1 + k1];
 #else
-#define SPX_TW(P) template <> SPX_HD cf tw<P>(int k) { return h_tw##P.w[k]; }
+    return HostTw2<C::P, C::E1>::t.w[n2 * C::E1 + k1];
 #endif
-SPX_TW(48) SPX_TW(96) SPX_TW(192) SPX_TW(384)
-#undef SPX_TW
+}
 
 // --------------------------------------------------------------------------
 // configuration
@@ -95,7 +90,7 @@ struct CcCfg {
     static constexpr size_t W_ELEMS = size_t(PL) * WP;
     static constexpr size_t S_ELEMS = INPLACE ? 0 : size_t(BATCH) * SP;
     static constexpr size_t R_ELEMS = size_t(RHL) * RP;
-    static_assert(CL == 1 || (CL == 2 && !INPLACE && WSM_ && RSM_ && E1 % 2 == 0),
+    static_assert(CL == 1 || (CL == 2 && WSM_ && RSM_ && E1 % 2 == 0),
                   "cluster mode: W and R in shared memory, even E1");
     static_assert(E1 * E2 == P, "P = E1*E2");
     static_assert(P % 2 == 0 && NMAX % 2 == 0, "even sizes");
@@ -425,7 +420,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
             static_for<0, C::E1>([&](auto K1) {
                 constexpr int k1 = decltype(K1)::value;
                 cf *wb = w_of_k1<C, k1>(c.W, c.Wpeer, c.rank);   // owner of the k1 group
-                wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gi] = cmul(x[k1], tw<C::P>(n2 * k1));
+                wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gi] = cmul(x[k1], tw2<C>(n2, k1));
             });
         }
     }
@@ -472,7 +467,7 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            c.W[(j * C::E2 + n2) * C::WP + l + col0] = cmulc(x[n2], tw<C::P>(n2 * k1));
+            c.W[(j * C::E2 + n2) * C::WP + l + col0] = cmulc(x[n2], tw2<C>(n2, k1));
         });
     }
 }
@@ -602,7 +597,7 @@ SPX_HD void x1_pass(const Ctx<C> &c, int tid, int cb, int ce, int xoff) {
         RegFFT<C::E1, false>::run(x);
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
-            srow[k1 * C::E2 + n2] = cmul(x[k1], tw<C::P>(n2 * k1));
+            srow[k1 * C::E2 + n2] = cmul(x[k1], tw2<C>(n2, k1));
         });
     }
 }
@@ -668,7 +663,7 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            srow[k1 * C::E2 + n2] = cmulc(x[n2], tw<C::P>(n2 * k1));
+            srow[k1 * C::E2 + n2] = cmulc(x[n2], tw2<C>(n2, k1));
         });
     }
 }

@@ -82,15 +82,18 @@ SPX_HD cf cmulc(cf a, cf b) {  // a * conj(b)
 }
 SPX_HD cf cconj(cf a) { return cmake(a.x, -a.y); }
 
-// ---- twiddle tables W_P^k = exp(-2*pi*i*k/P), k in [0, P) ---------------
-template <int P>
-struct TwTable {
+// Inter-stage twiddles of the two-step transform P = E1*E2, laid out so that the
+// runtime factor selects a base and the compile-time factor an immediate
+// offset: w[n2*E1 + k1] = W_P^(n2*k1), n2 in [0, E2), k1 in [0, E1).
+template <int P, int E1>
+struct TwTable2 {
     cf w[P];
-    constexpr TwTable() : w() {
-        for (int k = 0; k < P; ++k) {
-            w[k].x = float(cos2pi(k, P));
-            w[k].y = float(-sin2pi(k, P));
-        }
+    constexpr TwTable2() : w() {
+        for (int n2 = 0; n2 < P / E1; ++n2)
+            for (int k1 = 0; k1 < E1; ++k1) {
+                w[n2 * E1 + k1].x = float(cos2pi((long long)n2 * k1, P));
+                w[n2 * E1 + k1].y = float(-sin2pi((long long)n2 * k1, P));
+            }
     }
 };
 

@@ -190,6 +190,48 @@ int spx_find_peak(const void *surfaces, int kind, int n, int h, int w,
 int spx_segment_boxes(const void *seg, int seg_kind, int h, int w, int64_t pitch,
                       int max_label, int32_t *boxes_out, void *stream);
 
+/* ========================================================================
+ * (6) Batched blot of source (drizzled) cutouts onto target (image) cutout
+ * grids at several sub-pixel phases.
+ * Replaces blot.blot_cutout (blot.py:79-155; drizzlepac cdriz.tblot with
+ * interp='poly5', misval=0, kscale=1) as called four times per source by
+ * align.find_linear_fit (align.py:661-679: target grid displaced by half a
+ * pixel along x, along x and y, along y).
+ *
+ * src        ragged stack of float32 source cutouts (masked pixels already
+ *            zeroed, align.py:661); cutout k starts at element src_offset[k]
+ *            and has shape src_shape[k] = (h, w).
+ * map        [n,20] float64: xc, yc, a[3][3], b[3][3] - source position
+ *            (0-based pixels) of target pixel (x, y), u = x - xc, v = y - yc:
+ *              xs = sum_pq a[p][q] u^p v^q,  ys = sum_pq b[p][q] u^p v^q
+ *            (the host samples the WCS map of blot.py:21-76 on a 3x3 grid).
+ * phases_host [nph,2] float64 (ddx, ddy): phase k evaluates the map at
+ *            (i + ddx, j + ddy); nph <= 8.  align.py's four blots are
+ *            (0,0), (0.5,0), (0,0.5), (0.5,0.5) (Cutout.dx -= 0.5 moves the
+ *            grid by +0.5 px in the image frame, cutout.py:1112-1145).
+ * scale      [n] float32 or NULL: flux factor (ef / pix_ratio^2 and the
+ *            counts/rate conversions of blot.py:134-138,148-150).
+ * tgt_shape  [n,2] int32 (ny, nx); out_offset [n] int64: element offset of
+ *            phase 0 of cutout k in `out`; its phases follow contiguously
+ *            ([nph][ny][nx]).  max_ny, max_nx: largest target (grid sizing).
+ * Pixels that map outside [0, w-1] x [0, h-1] of their source get `misval`.
+ * ======================================================================== */
+#define SPX_BLOT_NEAREST 0
+#define SPX_BLOT_LINEAR  1
+#define SPX_BLOT_POLY5   2
+
+typedef struct spx_blot_args {
+    const float *src; const int64_t *src_offset; const int32_t *src_shape;
+    const double *map; const float *scale;
+    const int32_t *tgt_shape; const int64_t *out_offset;
+    float *out;
+    const double *phases_host;
+    int n, nph, interp, max_ny, max_nx;
+    float misval;
+} spx_blot_args;
+
+int spx_blot_phases(const spx_blot_args *args_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,9 @@ T_F32, T_F64, T_I8, T_I16, T_I32, T_I64 = 0, 1, 2, 3, 4, 5
 
 EXPORTS = ("spx_abi_version", "spx_error_string", "spx_gather_cutouts",
            "spx_cc_workspace_bytes", "spx_cc_fit_stack", "spx_cc_fit_frames",
-           "spx_find_peak", "spx_segment_boxes")
+           "spx_find_peak", "spx_segment_boxes", "spx_blot_phases")
+BLOT_NEAREST, BLOT_LINEAR, BLOT_POLY5 = 0, 1, 2
+BLOT_MAX_PHASES = 8
 
 
 class GatherArgs(C.Structure):
@@ -40,6 +42,20 @@ class GatherArgs(C.Structure):
         ("fillval", C.c_double), ("zero_masked", C.c_int),
         ("data_out", C.c_void_p), ("mask_out", C.c_void_p),
         ("dq_out", C.c_void_p), ("weight_out", C.c_void_p),
+    ]
+
+
+class BlotArgs(C.Structure):
+    """struct spx_blot_args"""
+    _fields_ = [
+        ("src", C.c_void_p), ("src_offset", C.c_void_p), ("src_shape", C.c_void_p),
+        ("map", C.c_void_p), ("scale", C.c_void_p),
+        ("tgt_shape", C.c_void_p), ("out_offset", C.c_void_p),
+        ("out", C.c_void_p),
+        ("phases_host", C.POINTER(C.c_double)),
+        ("n", C.c_int), ("nph", C.c_int), ("interp", C.c_int),
+        ("max_ny", C.c_int), ("max_nx", C.c_int),
+        ("misval", C.c_float),
     ]
 
 
@@ -83,6 +99,8 @@ def load():
                                   i32, i32, i32, i32, vp, vp, vp, vp]
     lib.spx_segment_boxes.restype = i32
     lib.spx_segment_boxes.argtypes = [vp, i32, i32, i32, i64, i32, vp, vp]
+    lib.spx_blot_phases.restype = i32
+    lib.spx_blot_phases.argtypes = [C.POINTER(BlotArgs), vp]
     if lib.spx_abi_version() != ABI_VERSION:
         raise RuntimeError("subpixal_b200: ABI version mismatch, rebuild the library")
     _lib = lib

@@ -7,9 +7,10 @@ four blots + one ``cc.find_displacement`` per source) into
     blot every source  ->  ONE batched CC + sub-pixel fit on the GPU  ->
     per-source WCS conversion  ->  linear fit
 
-The blot itself (drizzlepac ``cdriz.tblot`` behind ``subpixal.blot.blot_cutout``)
-is out of scope of this package: pass the
-reference's ``blot_cutout`` (or any callable with its signature) as ``blot``.
+By default the four blots of every source run on the GPU in one launch
+(``subpixal_b200.blot.blot_phases``) and feed the
+CC kernel without leaving the device; pass the reference's ``blot_cutout`` (or
+any callable with its signature) as ``blot`` to use drizzlepac's instead.
 
 ``iter_linear_fit`` restates the interface of ``tweakwcs.linearfit.iter_linear_fit``
 consumed at align.py:720-724 (tweakwcs is an un-vendored dependency that is not
@@ -132,8 +133,10 @@ def iter_linear_fit(xy, uv, wxy=None, wuv=None, fitgeom="general", center=None,
 # --------------------------------------------------------------------------
 def batched_displacements(stacks, cc_type="NCC", full_output=False):
     """``stacks``: sequence of ``(ref_image, image00, image10, image01, image11)``
-    tuples (numpy, shapes may differ between sources).  Sources are grouped by
-    shape, every group is one ``spx_cc_fit_stack`` launch.  Returns
+    tuples (numpy, shapes may differ between sources) or ``(ref_image, phases)``
+    pairs where ``phases`` is a CUDA float32 tensor ``[4, ny, nx]`` (the output of
+    ``blot.blot_phases``: the blots never leave the device).  Sources are grouped
+    by shape, every group is one ``spx_cc_fit_stack`` launch.  Returns
     ``(dxdy [n,2] float64, icc list or None)`` in input order (cc.py:21-95 per
     source)."""
     batch.require_cuda()
@@ -143,16 +146,33 @@ def batched_displacements(stacks, cc_type="NCC", full_output=False):
     groups = {}
     for k, st in enumerate(stacks):
         shp = tuple(np.shape(st[0]))
-        if any(tuple(np.shape(a)) != shp for a in st[1:]):
+        if len(st) == 2:
+            if tuple(st[1].shape) != (4,) + shp:
+                raise ValueError("All cutouts must have same shape.")
+        elif any(tuple(np.shape(a)) != shp for a in st[1:]):
             raise ValueError("All cutouts must have same shape.")       # cc.py:103-105
         groups.setdefault(shp, []).append(k)
     for shp, idx in groups.items():
-        host = np.empty((len(idx), 5) + shp, dtype=np.float32)
-        for j, k in enumerate(idx):
-            for s in range(5):
-                host[j, s] = stacks[k][s]
-        sh, _, _, icc = batch.cc_fit_stack(torch.from_numpy(host).cuda(), cc_type,
-                                           want_icc=full_output)
+        on_device = [len(stacks[k]) == 2 for k in idx]
+        if all(on_device):
+            refs = np.empty((len(idx),) + shp, dtype=np.float32)
+            for j, k in enumerate(idx):
+                refs[j] = stacks[k][0]
+            dev = stacks[idx[0]][1].device
+            stack = torch.empty((len(idx), 5) + shp, dtype=torch.float32, device=dev)
+            stack[:, 0] = torch.from_numpy(refs).to(dev)
+            for j, k in enumerate(idx):
+                stack[j, 1:] = stacks[k][1]
+        else:
+            host = np.empty((len(idx), 5) + shp, dtype=np.float32)
+            for j, k in enumerate(idx):
+                st = stacks[k]
+                if len(st) == 2:
+                    st = (st[0],) + tuple(st[1].cpu().numpy())
+                for s in range(5):
+                    host[j, s] = st[s]
+            stack = torch.from_numpy(host).cuda()
+        sh, _, _, icc = batch.cc_fit_stack(stack, cc_type, want_icc=full_output)
         dxdy[idx] = sh.cpu().numpy()
         if full_output:
             icc = icc.cpu().numpy()
@@ -166,7 +186,8 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
     """Linear fit to the cross-correlation displacements between ``img_cutouts``
     and the blots of ``drz_cutouts`` onto them (reference align.py:561-745; same
     parameters and return value ``(fit, interlaced_cc, nonshifted_blts)``).
-    ``blot(drz_cutout, img_cutout)`` must behave like ``subpixal.blot.blot_cutout``."""
+    ``blot``: None = batched GPU blot; else a callable ``blot(drz_cutout, img_cutout)``
+    that behaves like ``subpixal.blot.blot_cutout``, called four times per source."""
     if not hasattr(img_cutouts, "__iter__"):
         img_cutouts = [img_cutouts]
     if not hasattr(drz_cutouts, "__iter__"):
@@ -175,21 +196,27 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
     if len(img_cutouts) != len(drz_cutouts):
         raise ValueError("The number of image cutouts must match the number "
                          "of drizzled cutouts.")
-    if blot is None:
-        try:
-            from subpixal.blot import blot_cutout as blot
-        except ImportError:
-            raise RuntimeError("find_linear_fit needs a blot function "
-                               "(subpixal.blot.blot_cutout is not importable here).")
     if wcslin is None:
         wcslin = drz_cutouts[0].wcs                                   # align.py:636-638
     wcslin = wcslin.deepcopy()
     if any(getattr(wcslin, name, None) is not None for name in _WCS_DISTORTIONS):
         raise ValueError("Reference WCS must not have non-linear distortions.")
 
-    # ---- pass 1 (host / drizzlepac): the four half-pixel phase blots ----------
+    # ---- pass 1: the four half-pixel phase blots ------------------------------
     stacks, nonshifted = [], []
-    for imct, dzct in zip(img_cutouts, drz_cutouts):
+    if blot is None:
+        # GPU: every source and every phase in one launch (blot.blot_phases)
+        import copy
+        from . import blot as gpu_blot
+        for dzct in drz_cutouts:
+            dzct.data[dzct.mask] = 0                                   # align.py:661
+        phases = gpu_blot.blot_phases(drz_cutouts, img_cutouts)
+        for imct, ph in zip(img_cutouts, phases):
+            stacks.append((imct.data, ph))
+            blt00 = copy.deepcopy(imct)                                # blot.py:152-155
+            blt00.data[:, :] = ph[0].cpu().numpy()
+            nonshifted.append(blt00)
+    for imct, dzct in (() if blot is None else zip(img_cutouts, drz_cutouts)):
         dx0, dy0 = imct.dx, imct.dy
         dzct.data[dzct.mask] = 0                                       # align.py:661
         blt00 = blot(dzct, imct)

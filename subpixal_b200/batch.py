@@ -207,6 +207,81 @@ def gather_cutouts(frame, boxes, dq=None, weight=None, seg=None, src_ids=None,
     return out
 
 
+_BLOT_INTERP = {"nearest": L.BLOT_NEAREST, "linear": L.BLOT_LINEAR, "poly5": L.BLOT_POLY5}
+
+# align.py:664-679: blot to the image cutout, then with dx -= 0.5, dy -= 0.5 (both),
+# dy -= 0.5 alone.  Cutout.dx -= 0.5 moves the cutout grid by +0.5 px in the image
+# frame (cutout.py:1112-1145), so pixel i of the displaced blot samples the map of
+# the undisplaced cutout at i + 0.5.  Order = find_displacement's argument order.
+PHASES_00_10_01_11 = ((0.0, 0.0), (0.5, 0.0), (0.0, 0.5), (0.5, 0.5))
+
+
+def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00_10_01_11,
+                scale=None, interp="poly5", misval=0.0):
+    """Batched blot (reference blot.py:79-155 through cdriz.tblot; the four
+    half-pixel phases of align.py:661-679 in one launch).
+
+    ``src``: flat float32 CUDA tensor with the (masked-pixels-zeroed) source
+    cutouts, cutout k at ``src_offsets[k]`` with shape ``src_shapes[k] = (h, w)``;
+    ``maps``: ``[n, 20]`` float64 biquadratic target->source pixel maps (see
+    ``include/subpixal_b200.h``); ``tgt_shapes``: ``[n, 2]`` (ny, nx).
+    Returns ``(out, out_offsets)``: flat float32 tensor holding ``[nph, ny, nx]``
+    per cutout and the int64 ``[n+1]`` offsets (CPU)."""
+    require_cuda()
+    lib = L.load()
+    if interp not in _BLOT_INTERP:
+        raise ValueError("interp %r is not supported on the GPU (nearest, linear, poly5)"
+                         % (interp,))
+    src = _f32c(src, "src").reshape(-1)
+    dev = src.device
+    cpu = lambda t, dt: torch.as_tensor(t).to(dtype=dt, device="cpu").contiguous()
+    s_off = cpu(src_offsets, torch.int64).reshape(-1)
+    s_shp = cpu(src_shapes, torch.int32).reshape(-1, 2)
+    t_shp = cpu(tgt_shapes, torch.int32).reshape(-1, 2)
+    mp = cpu(maps, torch.float64).reshape(-1, 20)
+    n = int(t_shp.shape[0])
+    if not (s_shp.shape[0] == n and mp.shape[0] == n and s_off.numel() >= n):
+        raise ValueError("src_offsets, src_shapes, maps and tgt_shapes must describe n cutouts")
+    s_off = s_off[:n].contiguous()
+    ph = [(float(a), float(b)) for a, b in phases]
+    nph = len(ph)
+    if not 1 <= nph <= L.BLOT_MAX_PHASES:
+        raise ValueError("between 1 and %d phases" % L.BLOT_MAX_PHASES)
+    if n and (int(s_shp.min()) < 1 or int(t_shp.min()) < 1):
+        raise ValueError("Cutouts must be 2D images.")
+    if n and int((s_off + s_shp[:, 0].long() * s_shp[:, 1].long()).max()) > src.numel():
+        raise ValueError("source cutouts exceed the src buffer")
+    sizes = t_shp[:, 0].long() * t_shp[:, 1].long() * nph
+    o_off = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(sizes, 0, out=o_off[1:])
+    with torch.cuda.device(dev):
+        out = torch.empty(int(o_off[-1]), dtype=torch.float32, device=dev)
+        if n == 0:
+            return out, o_off
+        keep = [s_off.to(dev), s_shp.to(dev), mp.to(dev), t_shp.to(dev),
+                o_off[:-1].contiguous().to(dev)]
+        d_scale = None
+        if scale is not None:
+            d_scale = cpu(scale, torch.float32).reshape(-1)
+            if d_scale.numel() != n:
+                raise ValueError("scale must have one entry per cutout")
+            d_scale = d_scale.to(dev)
+        a = L.BlotArgs()
+        a.src = src.data_ptr()
+        a.src_offset, a.src_shape = keep[0].data_ptr(), keep[1].data_ptr()
+        a.map, a.tgt_shape, a.out_offset = keep[2].data_ptr(), keep[3].data_ptr(), keep[4].data_ptr()
+        a.scale = d_scale.data_ptr() if d_scale is not None else None
+        a.out = out.data_ptr()
+        flat = (C.c_double * (2 * nph))(*[v for p2 in ph for v in p2])
+        a.phases_host = C.cast(flat, C.POINTER(C.c_double))
+        a.n, a.nph, a.interp = n, nph, _BLOT_INTERP[interp]
+        a.max_ny, a.max_nx = int(t_shp[:, 0].max()), int(t_shp[:, 1].max())
+        a.misval = float(misval)
+        # the argument tables are freed in stream order by the caching allocator
+        L.check(lib.spx_blot_phases(C.byref(a), _stream()))
+    return out, o_off
+
+
 def find_peak_batch(surfaces, mask=None, guess=None, search_box=(0, 0),
                     fit_box=(5, 5)):
     """Batched centroid.find_peak (reference centroid.py:18-236) on a

@@ -1,0 +1,209 @@
+// (6) Batched blot of drizzled cutouts onto image-cutout grids at several
+// sub-pixel phases (reference blot.py:79-155 `blot_cutout` -> drizzlepac
+// `cdriz.tblot`, interp='poly5', misval=0; called four times per source at
+// align.py:661-679 with the target grid displaced by half a pixel).
+//
+// Per output pixel: target pixel (i + ddx, j + ddy) -> source position through a
+// per-source biquadratic map (float64, rounded once to float32 as drizzle's
+// pixmap is), range test against the source cutout, 6x6 quintic interpolation in
+// Everett's central-difference form with the linear edge extension
+// 2*f(edge) - f(mirror), flux scale.  All float32 arithmetic uses explicit
+// round-to-nearest intrinsics (no FMA contraction) in the operation order of
+// oracle/blot_oracle.py, so results are bit-identical to that restatement.
+//
+// Work decomposition: blockIdx.y = source, all phases of one source are produced by
+// the same CTAs (its source cutout stays in L1), lanes run along x so stores are
+// coalesced and the 36 loads of neighbouring lanes hit the same lines.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/subpixal_b200.h"
+
+namespace spx {
+
+constexpr int kBlotThreads = 256;
+constexpr int kMaxPhases = 8;
+
+struct BlotDev {
+    const float *src; const long long *src_off; const int *src_shape;
+    const double *map; const float *scale;
+    const int *tgt_shape; const long long *out_off;
+    float *out;
+    int n, nph, interp;
+    float misval;
+    double ph[kMaxPhases][2];
+};
+
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+
+// quintic through six equally spaced samples (positions -2..3) at 0 <= s < 1
+__device__ __forceinline__ float everett(float fm2, float fm1, float f0, float f1, float f2,
+                                         float f3, float s) {
+    const float s2 = fm(s, s), t = fs(1.f, s), t2 = fm(t, t);
+    const float cd20 = fm(1.0f / 6.0f, fa(fs(f1, fm(2.f, f0)), fm1));
+    const float cd21 = fm(1.0f / 6.0f, fa(fs(f2, fm(2.f, f1)), f0));
+    const float cd40 = fm(1.0f / 120.0f,
+                          fa(fs(fa(fs(fm2, fm(4.f, fm1)), fm(6.f, f0)), fm(4.f, f1)), f2));
+    const float cd41 = fm(1.0f / 120.0f,
+                          fa(fs(fa(fs(fm1, fm(4.f, f0)), fm(6.f, f1)), fm(4.f, f2)), f3));
+    const float a = fm(s, fa(f1, fm(fs(s2, 1.f), fa(cd21, fm(fs(s2, 4.f), cd41)))));
+    const float b = fm(t, fa(f0, fm(fs(t2, 1.f), fa(cd20, fm(fs(t2, 4.f), cd40)))));
+    return fa(a, b);
+}
+
+struct Fold { int m, e; bool out; };
+__device__ __forceinline__ Fold fold(int k, int n) {
+    Fold f;
+    const bool lo = k < 0, hi = k >= n;
+    int m = lo ? -k : (hi ? 2 * (n - 1) - k : k);
+    m = m < 0 ? 0 : (m > n - 1 ? n - 1 : m);
+    f.m = m; f.e = lo ? 0 : (hi ? n - 1 : k); f.out = lo || hi;
+    return f;
+}
+
+// source sample with the linear edge extension, columns first, then rows
+__device__ __forceinline__ float ext_sample(const float *d, int h, int w, int j, int i) {
+    const Fold fx = fold(i, w), fy = fold(j, h);
+    auto col = [&](int row) {
+        const float direct = __ldg(d + (long long)row * w + fx.m);
+        return fx.out ? fs(fm(2.f, __ldg(d + (long long)row * w + fx.e)), direct) : direct;
+    };
+    const float direct = col(fy.m);
+    return fy.out ? fs(fm(2.f, col(fy.e)), direct) : direct;
+}
+
+__device__ __forceinline__ float poly5(const float *d, int h, int w, float x, float y) {
+    const int ix = int(x), iy = int(y);
+    const float sx = fs(x, float(ix)), sy = fs(y, float(iy));
+    float z[6];
+    if (ix >= 2 && ix + 3 < w && iy >= 2 && iy + 3 < h) {           // interior: plain loads
+        const float *p = d + (long long)(iy - 2) * w + (ix - 2);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            float f[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) f[c] = __ldg(p + (long long)r * w + c);
+            z[r] = everett(f[0], f[1], f[2], f[3], f[4], f[5], sx);
+        }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < 6; ++r) {
+            float f[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) f[c] = ext_sample(d, h, w, iy - 2 + r, ix - 2 + c);
+            z[r] = everett(f[0], f[1], f[2], f[3], f[4], f[5], sx);
+        }
+    }
+    return everett(z[0], z[1], z[2], z[3], z[4], z[5], sy);
+}
+
+__device__ __forceinline__ float bilinear(const float *d, int h, int w, float x, float y) {
+    const int ix = int(x), iy = int(y);
+    const float sx = fs(x, float(ix)), sy = fs(y, float(iy));
+    const float tx = fs(1.f, sx), ty = fs(1.f, sy);
+    const int i1 = ix + 1 < w ? ix + 1 : w - 1, j1 = iy + 1 < h ? iy + 1 : h - 1;
+    const float d00 = __ldg(d + (long long)iy * w + ix), d10 = __ldg(d + (long long)iy * w + i1);
+    const float d01 = __ldg(d + (long long)j1 * w + ix), d11 = __ldg(d + (long long)j1 * w + i1);
+    return fa(fa(fa(fm(fm(tx, ty), d00), fm(fm(sx, ty), d10)), fm(fm(tx, sy), d01)),
+              fm(fm(sx, sy), d11));
+}
+
+__device__ __forceinline__ float nearest(const float *d, int h, int w, float x, float y) {
+    int ix = int(fa(x, 0.5f)), iy = int(fa(y, 0.5f));
+    ix = ix < w ? ix : w - 1; iy = iy < h ? iy : h - 1;
+    return __ldg(d + (long long)iy * w + ix);
+}
+
+__device__ __forceinline__ double dma(double a, double b, double c) {   // a*b + c, two roundings
+    return __dadd_rn(__dmul_rn(a, b), c);
+}
+
+template <int INTERP>
+__global__ void __launch_bounds__(kBlotThreads) blot_kernel(const BlotDev a) {
+    const int s = blockIdx.y;
+    const int h = a.src_shape[2 * s], w = a.src_shape[2 * s + 1];
+    const int ny = a.tgt_shape[2 * s], nx = a.tgt_shape[2 * s + 1];
+    if (h < 1 || w < 1 || ny < 1 || nx < 1) return;
+    const float *d = a.src + a.src_off[s];
+    float *out = a.out + a.out_off[s];
+    const double *cf = a.map + 20 * (long long)s;
+    const double xc = cf[0], yc = cf[1];
+    const float scale = a.scale ? a.scale[s] : 1.f;
+    const float xmax = float(w - 1), ymax = float(h - 1);
+    // items = (phase, row, 32-pixel segment); a warp owns one item at a time
+    const int segs = (nx + 31) >> 5;
+    const int items = a.nph * ny * segs;
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * (kBlotThreads / 32) + (threadIdx.x >> 5);
+    const int wstride = gridDim.x * (kBlotThreads / 32);
+    for (int it = wid; it < items; it += wstride) {
+        const int seg = it % segs, rowph = it / segs;
+        const int j = rowph % ny, k = rowph / ny;
+        const int i = seg * 32 + lane;
+        if (i >= nx) continue;
+        const double u = __dsub_rn(__dadd_rn(double(i), a.ph[k][0]), xc);
+        const double v = __dsub_rn(__dadd_rn(double(j), a.ph[k][1]), yc);
+        double xy[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double *c = cf + 2 + 9 * q;
+            const double r0 = dma(dma(c[2], v, c[1]), v, c[0]);
+            const double r1 = dma(dma(c[5], v, c[4]), v, c[3]);
+            const double r2 = dma(dma(c[8], v, c[7]), v, c[6]);
+            xy[q] = dma(dma(r2, u, r1), u, r0);
+        }
+        const float x = __double2float_rn(xy[0]), y = __double2float_rn(xy[1]);
+        float val = a.misval;
+        if (x >= 0.f && x <= xmax && y >= 0.f && y <= ymax) {
+            float t;
+            if (INTERP == SPX_BLOT_POLY5) t = poly5(d, h, w, x, y);
+            else if (INTERP == SPX_BLOT_LINEAR) t = bilinear(d, h, w, x, y);
+            else t = nearest(d, h, w, x, y);
+            val = fm(t, scale);
+        }
+        out[((long long)k * ny + j) * nx + i] = val;
+    }
+}
+
+}  // namespace spx
+
+extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
+    using namespace spx;
+    if (!args_host) return SPX_E_BADARG;
+    const spx_blot_args &g = *args_host;
+    if (g.n < 0 || g.nph < 1 || g.nph > kMaxPhases || !g.phases_host) return SPX_E_BADARG;
+    if (g.n == 0) return 0;
+    if (!g.src || !g.src_offset || !g.src_shape || !g.map || !g.tgt_shape || !g.out_offset ||
+        !g.out || g.max_ny < 1 || g.max_nx < 1)
+        return SPX_E_BADARG;
+    if (g.interp != SPX_BLOT_NEAREST && g.interp != SPX_BLOT_LINEAR && g.interp != SPX_BLOT_POLY5)
+        return SPX_E_UNSUPPORTED;
+    if (g.n > 65535 * 64) return SPX_E_UNSUPPORTED;
+    BlotDev a;
+    a.src = g.src; a.src_off = reinterpret_cast<const long long *>(g.src_offset);
+    a.src_shape = g.src_shape; a.map = g.map; a.scale = g.scale;
+    a.tgt_shape = g.tgt_shape; a.out_off = reinterpret_cast<const long long *>(g.out_offset);
+    a.out = g.out; a.nph = g.nph; a.interp = g.interp; a.misval = g.misval;
+    for (int k = 0; k < g.nph; ++k) { a.ph[k][0] = g.phases_host[2 * k]; a.ph[k][1] = g.phases_host[2 * k + 1]; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // CTAs per source: enough warps for the largest target, at most 8 items per warp
+    const long long items = (long long)g.nph * g.max_ny * ((g.max_nx + 31) / 32);
+    int bx = int((items + 8 * (kBlotThreads / 32) - 1) / (8 * (kBlotThreads / 32)));
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    for (int s0 = 0; s0 < g.n; s0 += 65535) {               // gridDim.y limit
+        const int cnt = g.n - s0 < 65535 ? g.n - s0 : 65535;
+        BlotDev b = a;
+        b.n = cnt;
+        b.src_off += s0; b.src_shape += 2 * s0; b.map += 20 * (long long)s0;
+        if (b.scale) b.scale += s0;
+        b.tgt_shape += 2 * s0; b.out_off += s0;
+        const dim3 grid(bx, cnt);
+        if (g.interp == SPX_BLOT_POLY5) blot_kernel<SPX_BLOT_POLY5><<<grid, kBlotThreads, 0, st>>>(b);
+        else if (g.interp == SPX_BLOT_LINEAR) blot_kernel<SPX_BLOT_LINEAR><<<grid, kBlotThreads, 0, st>>>(b);
+        else blot_kernel<SPX_BLOT_NEAREST><<<grid, kBlotThreads, 0, st>>>(b);
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : int(e);
+}

@@ -215,6 +215,13 @@ int spx_segment_boxes(const void *seg, int seg_kind, int h, int w, int64_t pitch
  *            phase 0 of cutout k in `out`; its phases follow contiguously
  *            ([nph][ny][nx]).  max_ny, max_nx: largest target (grid sizing).
  * Pixels that map outside [0, w-1] x [0, h-1] of their source get `misval`.
+ * workspace  optional (poly5 only): 16-byte aligned scratch in which the sources
+ *            are prepared once (edge-extended sample + its x-direction central
+ *            differences per pixel) so that the four phases share that work;
+ *            source k uses spx_blot_workspace_bytes(h_k, w_k) bytes starting at
+ *            16 * ws_offset[k] (ws_offset [n] int64, in 16-byte units);
+ *            max_src_h/max_src_w: largest source.  NULL = direct evaluation.
+ *            Results are bit-identical either way.
  * ======================================================================== */
 #define SPX_BLOT_NEAREST 0
 #define SPX_BLOT_LINEAR  1
@@ -228,8 +235,10 @@ typedef struct spx_blot_args {
     const double *phases_host;
     int n, nph, interp, max_ny, max_nx;
     float misval;
+    void *workspace; const int64_t *ws_offset; int max_src_h, max_src_w;
 } spx_blot_args;
 
+size_t spx_blot_workspace_bytes(int src_h, int src_w);
 int spx_blot_phases(const spx_blot_args *args_host, void *stream);
 
 #ifdef __cplusplus

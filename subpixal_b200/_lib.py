@@ -22,7 +22,8 @@ T_F32, T_F64, T_I8, T_I16, T_I32, T_I64 = 0, 1, 2, 3, 4, 5
 
 EXPORTS = ("spx_abi_version", "spx_error_string", "spx_gather_cutouts",
            "spx_cc_workspace_bytes", "spx_cc_fit_stack", "spx_cc_fit_frames",
-           "spx_find_peak", "spx_segment_boxes", "spx_blot_phases")
+           "spx_find_peak", "spx_segment_boxes", "spx_blot_phases",
+           "spx_blot_workspace_bytes")
 BLOT_NEAREST, BLOT_LINEAR, BLOT_POLY5 = 0, 1, 2
 BLOT_MAX_PHASES = 8
 
@@ -56,6 +57,8 @@ class BlotArgs(C.Structure):
         ("n", C.c_int), ("nph", C.c_int), ("interp", C.c_int),
         ("max_ny", C.c_int), ("max_nx", C.c_int),
         ("misval", C.c_float),
+        ("workspace", C.c_void_p), ("ws_offset", C.c_void_p),
+        ("max_src_h", C.c_int), ("max_src_w", C.c_int),
     ]
 
 
@@ -99,6 +102,8 @@ def load():
                                   i32, i32, i32, i32, vp, vp, vp, vp]
     lib.spx_segment_boxes.restype = i32
     lib.spx_segment_boxes.argtypes = [vp, i32, i32, i32, i64, i32, vp, vp]
+    lib.spx_blot_workspace_bytes.restype = sz
+    lib.spx_blot_workspace_bytes.argtypes = [i32, i32]
     lib.spx_blot_phases.restype = i32
     lib.spx_blot_phases.argtypes = [C.POINTER(BlotArgs), vp]
     if lib.spx_abi_version() != ABI_VERSION:

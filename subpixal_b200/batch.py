@@ -217,7 +217,7 @@ PHASES_00_10_01_11 = ((0.0, 0.0), (0.5, 0.0), (0.0, 0.5), (0.5, 0.5))
 
 
 def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00_10_01_11,
-                scale=None, interp="poly5", misval=0.0):
+                scale=None, interp="poly5", misval=0.0, prepare=True):
     """Batched blot (reference blot.py:79-155 through cdriz.tblot; the four
     half-pixel phases of align.py:661-679 in one launch).
 
@@ -226,7 +226,9 @@ def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00
     ``maps``: ``[n, 20]`` float64 biquadratic target->source pixel maps (see
     ``include/subpixal_b200.h``); ``tgt_shapes``: ``[n, 2]`` (ny, nx).
     Returns ``(out, out_offsets)``: flat float32 tensor holding ``[nph, ny, nx]``
-    per cutout and the int64 ``[n+1]`` offsets (CPU)."""
+    per cutout and the int64 ``[n+1]`` offsets (CPU).  ``prepare``: (poly5) tabulate
+    the sources' x-direction central differences once in a scratch buffer shared by
+    all phases (16 B per source pixel; bit-identical results, about twice as fast)."""
     require_cuda()
     lib = L.load()
     if interp not in _BLOT_INTERP:
@@ -277,6 +279,16 @@ def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00
         a.n, a.nph, a.interp = n, nph, _BLOT_INTERP[interp]
         a.max_ny, a.max_nx = int(t_shp[:, 0].max()), int(t_shp[:, 1].max())
         a.misval = float(misval)
+        if prepare and interp == "poly5":
+            # spx_blot_workspace_bytes(h, w) / 16 = (h + 5) * (w + 1) float4 per source
+            units = (s_shp[:, 0].long() + 5) * (s_shp[:, 1].long() + 1)
+            w_off = torch.zeros(n + 1, dtype=torch.int64)
+            torch.cumsum(units, 0, out=w_off[1:])
+            assert int(units[0]) * 16 == lib.spx_blot_workspace_bytes(int(s_shp[0, 0]), int(s_shp[0, 1]))
+            ws = torch.empty(int(w_off[-1]) * 4, dtype=torch.float32, device=dev)
+            keep += [ws, w_off[:-1].contiguous().to(dev)]
+            a.workspace, a.ws_offset = ws.data_ptr(), keep[-1].data_ptr()
+            a.max_src_h, a.max_src_w = int(s_shp[:, 0].max()), int(s_shp[:, 1].max())
         # the argument tables are freed in stream order by the caching allocator
         L.check(lib.spx_blot_phases(C.byref(a), _stream()))
     return out, o_off

@@ -28,6 +28,7 @@ struct BlotDev {
     const double *map; const float *scale;
     const int *tgt_shape; const long long *out_off;
     float *out;
+    float4 *ws; const long long *ws_off;      // prepared sources (poly5), see blot_prep_kernel
     int n, nph, interp;
     float misval;
     double ph[kMaxPhases][2];
@@ -98,6 +99,74 @@ __device__ __forceinline__ float poly5(const float *d, int h, int w, float x, fl
     return everett(z[0], z[1], z[2], z[3], z[4], z[5], sy);
 }
 
+// ---- prepared sources ------------------------------------------------------------
+// The x-direction central differences of Everett's formula belong to the SOURCE
+// sample, not to the output pixel: cd2(c) = (E(c+1) - 2E(c) + E(c-1))/6 and
+// cd4(c) = (E(c-2) - 4E(c-1) + 6E(c) - 4E(c+1) + E(c+2))/120 with E the edge-
+// extended source.  blot_prep_kernel evaluates them once per source pixel on the
+// padded domain rows [-2, h+2] x columns [0, w] and stores {E, cd2, cd4, 0} as one
+// float4, so the main kernel needs two 128-bit loads and 15 operations per stencil
+// row instead of six loads and 41 operations.  Same operations in the same order:
+// results are bit-identical to the direct form.
+constexpr int kPadRows = 5;      // rows -2 .. h+2
+__host__ __device__ __forceinline__ long long prep_elems(int h, int w) {
+    return (long long)(h + kPadRows) * (w + 1);
+}
+
+__global__ void __launch_bounds__(kBlotThreads) blot_prep_kernel(const BlotDev a) {
+    const int s = blockIdx.y;
+    const int h = a.src_shape[2 * s], w = a.src_shape[2 * s + 1];
+    if (h < 1 || w < 1) return;
+    const float *d = a.src + a.src_off[s];
+    float4 *ws = a.ws + a.ws_off[s];
+    const int pw = w + 1, total = (h + kPadRows) * pw;
+    for (int t = blockIdx.x * kBlotThreads + threadIdx.x; t < total; t += gridDim.x * kBlotThreads) {
+        const int r = t / pw, c = t - r * pw;
+        const int j = r - 2;
+        float e[5];
+        if (j >= 0 && j < h && c >= 2 && c + 2 < w) {                 // interior: plain loads
+            const float *p = d + (long long)j * w + (c - 2);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) e[k] = __ldg(p + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) e[k] = ext_sample(d, h, w, j, c - 2 + k);
+        }
+        float4 o;
+        o.x = e[2];
+        o.y = fm(1.0f / 6.0f, fa(fs(e[3], fm(2.f, e[2])), e[1]));
+        o.z = fm(1.0f / 120.0f, fa(fs(fa(fs(e[0], fm(4.f, e[1])), fm(6.f, e[2])), fm(4.f, e[3])), e[4]));
+        o.w = 0.f;
+        ws[t] = o;
+    }
+}
+
+// one stencil row from the prepared source: samples at columns ix (p0) and ix+1 (p1)
+__device__ __forceinline__ float everett_row(float4 p0, float4 p1, float s, float s2m1, float s2m4,
+                                             float t, float t2m1, float t2m4) {
+    const float a = fm(s, fa(p1.x, fm(s2m1, fa(p1.y, fm(s2m4, p1.z)))));
+    const float b = fm(t, fa(p0.x, fm(t2m1, fa(p0.y, fm(t2m4, p0.z)))));
+    return fa(a, b);
+}
+
+__device__ __forceinline__ float poly5_prepared(const float4 *ws, int w, float x, float y) {
+    const int ix = int(x), iy = int(y);
+    const float sx = fs(x, float(ix)), sy = fs(y, float(iy));
+    const float s2 = fm(sx, sx), t = fs(1.f, sx), t2 = fm(t, t);
+    const float s2m1 = fs(s2, 1.f), s2m4 = fs(s2, 4.f), t2m1 = fs(t2, 1.f), t2m4 = fs(t2, 4.f);
+    const float4 *p = ws + (long long)iy * (w + 1) + ix;       // padded row iy = source row iy-2
+    float4 q[12];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        q[2 * r] = __ldg(p + (long long)r * (w + 1));
+        q[2 * r + 1] = __ldg(p + (long long)r * (w + 1) + 1);
+    }
+    float z[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) z[r] = everett_row(q[2 * r], q[2 * r + 1], sx, s2m1, s2m4, t, t2m1, t2m4);
+    return everett(z[0], z[1], z[2], z[3], z[4], z[5], sy);
+}
+
 __device__ __forceinline__ float bilinear(const float *d, int h, int w, float x, float y) {
     const int ix = int(x), iy = int(y);
     const float sx = fs(x, float(ix)), sy = fs(y, float(iy));
@@ -119,7 +188,7 @@ __device__ __forceinline__ double dma(double a, double b, double c) {   // a*b +
     return __dadd_rn(__dmul_rn(a, b), c);
 }
 
-template <int INTERP>
+template <int INTERP, bool PREP>
 __global__ void __launch_bounds__(kBlotThreads) blot_kernel(const BlotDev a) {
     const int s = blockIdx.y;
     const int h = a.src_shape[2 * s], w = a.src_shape[2 * s + 1];
@@ -127,46 +196,61 @@ __global__ void __launch_bounds__(kBlotThreads) blot_kernel(const BlotDev a) {
     if (h < 1 || w < 1 || ny < 1 || nx < 1) return;
     const float *d = a.src + a.src_off[s];
     float *out = a.out + a.out_off[s];
-    const double *cf = a.map + 20 * (long long)s;
+    const float4 *ws = PREP ? a.ws + a.ws_off[s] : nullptr;
+    // the map's 20 coefficients: shared memory, re-read at the start of every row
+    __shared__ double cf[20];
+    if (threadIdx.x < 20) cf[threadIdx.x] = __ldg(a.map + 20 * (long long)s + threadIdx.x);
+    __syncthreads();
     const double xc = cf[0], yc = cf[1];
     const float scale = a.scale ? a.scale[s] : 1.f;
     const float xmax = float(w - 1), ymax = float(h - 1);
     // items = (phase, row, 32-pixel segment); a warp owns one item at a time
     const int segs = (nx + 31) >> 5;
-    const int items = a.nph * ny * segs;
+    const int rows = a.nph * ny;
     const int lane = threadIdx.x & 31;
     const int wid = blockIdx.x * (kBlotThreads / 32) + (threadIdx.x >> 5);
     const int wstride = gridDim.x * (kBlotThreads / 32);
-    for (int it = wid; it < items; it += wstride) {
-        const int seg = it % segs, rowph = it / segs;
-        const int j = rowph % ny, k = rowph / ny;
-        const int i = seg * 32 + lane;
-        if (i >= nx) continue;
-        const double u = __dsub_rn(__dadd_rn(double(i), a.ph[k][0]), xc);
+    for (int rowph = wid; rowph < rows; rowph += wstride) {
+        const int k = rowph / ny, j = rowph - k * ny;
+        const double phx = a.ph[k][0];
         const double v = __dsub_rn(__dadd_rn(double(j), a.ph[k][1]), yc);
-        double xy[2];
+        // Horner in v is shared by the whole row
+        double r[2][3];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const double *c = cf + 2 + 9 * q;
-            const double r0 = dma(dma(c[2], v, c[1]), v, c[0]);
-            const double r1 = dma(dma(c[5], v, c[4]), v, c[3]);
-            const double r2 = dma(dma(c[8], v, c[7]), v, c[6]);
-            xy[q] = dma(dma(r2, u, r1), u, r0);
+            r[q][0] = dma(dma(c[2], v, c[1]), v, c[0]);
+            r[q][1] = dma(dma(c[5], v, c[4]), v, c[3]);
+            r[q][2] = dma(dma(c[8], v, c[7]), v, c[6]);
         }
+        float *orow = out + ((long long)k * ny + j) * nx;
+      for (int seg = 0; seg < segs; ++seg) {
+        const int i = seg * 32 + lane;
+        if (i >= nx) continue;
+        const double u = __dsub_rn(__dadd_rn(double(i), phx), xc);
+        double xy[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) xy[q] = dma(dma(r[q][2], u, r[q][1]), u, r[q][0]);
         const float x = __double2float_rn(xy[0]), y = __double2float_rn(xy[1]);
         float val = a.misval;
         if (x >= 0.f && x <= xmax && y >= 0.f && y <= ymax) {
             float t;
-            if (INTERP == SPX_BLOT_POLY5) t = poly5(d, h, w, x, y);
+            if (INTERP == SPX_BLOT_POLY5) t = PREP ? poly5_prepared(ws, w, x, y) : poly5(d, h, w, x, y);
             else if (INTERP == SPX_BLOT_LINEAR) t = bilinear(d, h, w, x, y);
             else t = nearest(d, h, w, x, y);
             val = fm(t, scale);
         }
-        out[((long long)k * ny + j) * nx + i] = val;
+        orow[i] = val;
+      }
     }
 }
 
 }  // namespace spx
+
+extern "C" size_t spx_blot_workspace_bytes(int src_h, int src_w) {
+    if (src_h < 1 || src_w < 1) return 0;
+    return size_t(spx::prep_elems(src_h, src_w)) * sizeof(float4);
+}
 
 extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
     using namespace spx;
@@ -185,11 +269,15 @@ extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
     a.src_shape = g.src_shape; a.map = g.map; a.scale = g.scale;
     a.tgt_shape = g.tgt_shape; a.out_off = reinterpret_cast<const long long *>(g.out_offset);
     a.out = g.out; a.nph = g.nph; a.interp = g.interp; a.misval = g.misval;
+    const bool prep = g.interp == SPX_BLOT_POLY5 && g.workspace != nullptr;
+    if (prep && (!g.ws_offset || g.max_src_h < 1 || g.max_src_w < 1)) return SPX_E_BADARG;
+    a.ws = static_cast<float4 *>(g.workspace);
+    a.ws_off = reinterpret_cast<const long long *>(g.ws_offset);
     for (int k = 0; k < g.nph; ++k) { a.ph[k][0] = g.phases_host[2 * k]; a.ph[k][1] = g.phases_host[2 * k + 1]; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // CTAs per source: enough warps for the largest target, at most 8 items per warp
+    // CTAs per source: a warp handles whole rows (phase, j), about 32 segments of 32 px each
     const long long items = (long long)g.nph * g.max_ny * ((g.max_nx + 31) / 32);
-    int bx = int((items + 8 * (kBlotThreads / 32) - 1) / (8 * (kBlotThreads / 32)));
+    int bx = int((items + 32 * (kBlotThreads / 32) - 1) / (32 * (kBlotThreads / 32)));
     if (bx < 1) bx = 1;
     if (bx > 64) bx = 64;
     for (int s0 = 0; s0 < g.n; s0 += 65535) {               // gridDim.y limit
@@ -199,10 +287,17 @@ extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
         b.src_off += s0; b.src_shape += 2 * s0; b.map += 20 * (long long)s0;
         if (b.scale) b.scale += s0;
         b.tgt_shape += 2 * s0; b.out_off += s0;
+        if (prep) b.ws_off += s0;
         const dim3 grid(bx, cnt);
-        if (g.interp == SPX_BLOT_POLY5) blot_kernel<SPX_BLOT_POLY5><<<grid, kBlotThreads, 0, st>>>(b);
-        else if (g.interp == SPX_BLOT_LINEAR) blot_kernel<SPX_BLOT_LINEAR><<<grid, kBlotThreads, 0, st>>>(b);
-        else blot_kernel<SPX_BLOT_NEAREST><<<grid, kBlotThreads, 0, st>>>(b);
+        if (prep) {
+            const long long pe = prep_elems(g.max_src_h, g.max_src_w);
+            int px = int((pe + 4 * kBlotThreads - 1) / (4 * kBlotThreads));
+            px = px < 1 ? 1 : (px > 64 ? 64 : px);
+            blot_prep_kernel<<<dim3(px, cnt), kBlotThreads, 0, st>>>(b);
+            blot_kernel<SPX_BLOT_POLY5, true><<<grid, kBlotThreads, 0, st>>>(b);
+        } else if (g.interp == SPX_BLOT_POLY5) blot_kernel<SPX_BLOT_POLY5, false><<<grid, kBlotThreads, 0, st>>>(b);
+        else if (g.interp == SPX_BLOT_LINEAR) blot_kernel<SPX_BLOT_LINEAR, false><<<grid, kBlotThreads, 0, st>>>(b);
+        else blot_kernel<SPX_BLOT_NEAREST, false><<<grid, kBlotThreads, 0, st>>>(b);
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : int(e);

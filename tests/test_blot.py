@@ -157,8 +157,9 @@ def _random_case(rng, k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("interp", ["poly5", "linear", "nearest"])
-def test_gpu_blot_is_bit_identical_to_the_oracle(interp):
+@pytest.mark.parametrize("interp,prepare", [("poly5", True), ("poly5", False), ("linear", False),
+                                            ("nearest", False)])
+def test_gpu_blot_is_bit_identical_to_the_oracle(interp, prepare):
     from subpixal_b200 import batch
     rng = np.random.default_rng(7)
     cases = [_random_case(rng, k) for k in range(24)]
@@ -173,7 +174,8 @@ def test_gpu_blot_is_bit_identical_to_the_oracle(interp):
     t_shp = np.array([c[2] for c in cases])
     scale = rng.uniform(0.5, 2.0, len(cases)).astype(np.float32)
     out, off = batch.blot_phases(torch.from_numpy(flat).cuda(), s_off, s_shp, maps, t_shp,
-                                 phases=PHASES, scale=scale, interp=interp, misval=-1.5)
+                                 phases=PHASES, scale=scale, interp=interp, misval=-1.5,
+                                 prepare=prepare)
     out = out.cpu().numpy()
     inside = 0
     for k, (src, coef, (ny, nx)) in enumerate(cases):

@@ -20,7 +20,12 @@ def main():
     except Exception: pass
     out = []
     g = torch.Generator(device="cuda").manual_seed(0)
-    for n_side, n in ((64, 10000), (128, 5000), (32, 50000)):
+    cases = ((64, 10000), (128, 5000), (32, 50000))
+    variants = (("poly5", True), ("poly5", False), ("linear", False))
+    if len(sys.argv) > 1:            # e.g.  blot_bench.py 64 poly5 1   (for ncu)
+        cases = tuple(c for c in cases if c[0] == int(sys.argv[1]))
+        variants = ((sys.argv[2], sys.argv[3] == "1"),)
+    for n_side, n in cases:
         hs = n_side + 16                     # source cutouts a little larger than the targets
         src = torch.randn((n * hs * hs,), device="cuda", generator=g)
         rng = np.random.default_rng(1)
@@ -28,8 +33,8 @@ def main():
                                  (x + a * y + t[0], y - a * x + t[1]), n_side, n_side) for _ in range(n)])
         s_shp = np.full((n, 2), hs); t_shp = np.full((n, 2), n_side)
         s_off = np.arange(n) * hs * hs
-        for interp in ("poly5", "linear"):
-            fn = lambda: batch.blot_phases(src, s_off, s_shp, maps, t_shp, interp=interp)
+        for interp, prep in variants:
+            fn = lambda: batch.blot_phases(src, s_off, s_shp, maps, t_shp, interp=interp, prepare=prep)
             for _ in range(2): fn()
             torch.cuda.synchronize()
             # device time of the kernel alone: the host-side table upload is outside the events
@@ -48,6 +53,10 @@ def main():
             ph = (C.c_double * 8)(0, 0, .5, 0, 0, .5, .5, .5)
             a.phases_host = C.cast(ph, C.POINTER(C.c_double))
             a.n, a.nph, a.interp, a.max_ny, a.max_nx = n, 4, {"poly5": 2, "linear": 1}[interp], n_side, n_side
+            if prep:
+                ws = torch.empty(n * (hs + 5) * (hs + 1) * 4, device=dev)
+                wo = (torch.arange(n, dtype=torch.int64) * (hs + 5) * (hs + 1)).to(dev)
+                a.workspace, a.ws_offset, a.max_src_h, a.max_src_w = ws.data_ptr(), wo.data_ptr(), hs, hs
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             for _ in range(3): L.check(lib.spx_blot_phases(C.byref(a), st))
             torch.cuda.synchronize()
@@ -57,7 +66,7 @@ def main():
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
             by = n * (hs * hs * 4 + 4 * n_side * n_side * 4)
-            out.append({"kernel": "blot_kernel<%s> x4 phases" % interp, "n": n, "target": n_side, "source": hs,
+            out.append({"kernel": "blot_kernel<%s%s> x4 phases" % (interp, ", prepared" if prep else ""), "n": n, "target": n_side, "source": hs,
                         "ms": ms, "sources_per_s": n / ms * 1e3, "Mpix_per_s": n * 4 * n_side * n_side / ms / 1e3,
                         "algorithmic_GB": by / 1e9, "GBps": by / ms / 1e6, "hbm_frac": by / ms / 1e6 / peak})
             print(out[-1], flush=True)

@@ -141,6 +141,24 @@ int spx_cc_fit_stack(const float *ref, const float *im00, const float *im10,
                      float *icc, void *workspace, size_t workspace_bytes,
                      void *stream);
 
+/* (2b) The same for cutouts of DIFFERENT shapes (the bounding-box cutouts of
+ * create_cutouts are ragged, cutout.py:159-175): pair p occupies the
+ * contiguous block [5][ny_p][nx_p] (ref_image, image00, image10, image01,
+ * image11) at element offsets[p] of `stack`, shapes[p] = (ny_p, nx_p).
+ * order      [n] int32 device: the pairs this launch processes (outputs are
+ *            written at index p = order[k], so several launches can fill one
+ *            table), or NULL for 0..n-1.  Every processed pair must fit the
+ *            size class of (max_ny, max_nx) - 32, 64, 128 or 256 px; the
+ *            caller buckets pairs by class (one launch per class) because a
+ *            pair costs as much as the largest shape of its class.
+ * icc        ragged output: surface p at element icc_offsets[p], or NULL.
+ * workspace  spx_cc_workspace_bytes(n, max_ny, max_nx, icc != NULL) bytes. */
+int spx_cc_fit_ragged(const float *stack, const int64_t *offsets, const int32_t *shapes,
+                      const int32_t *order, int n, int max_ny, int max_nx, int cc_type,
+                      double *shifts, int32_t *peak, int32_t *status,
+                      float *icc, const int64_t *icc_offsets,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* ========================================================================
  * (3) Fused gather + cross-correlation + fit straight from full frames.
  * = (1) with fillval 0 for five frames sharing one box table, feeding (2)

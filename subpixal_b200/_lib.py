@@ -21,7 +21,8 @@ S_FIT_NONFINITE, S_BOX_MISMATCH, S_FEW_POINTS, S_SINGULAR = 0x200, 0x400, 0x800,
 T_F32, T_F64, T_I8, T_I16, T_I32, T_I64 = 0, 1, 2, 3, 4, 5
 
 EXPORTS = ("spx_abi_version", "spx_error_string", "spx_gather_cutouts",
-           "spx_cc_workspace_bytes", "spx_cc_fit_stack", "spx_cc_fit_frames",
+           "spx_cc_workspace_bytes", "spx_cc_fit_stack", "spx_cc_fit_ragged",
+           "spx_cc_fit_frames",
            "spx_find_peak", "spx_segment_boxes", "spx_blot_phases",
            "spx_blot_workspace_bytes")
 BLOT_NEAREST, BLOT_LINEAR, BLOT_POLY5 = 0, 1, 2
@@ -93,6 +94,9 @@ def load():
     lib.spx_cc_fit_stack.restype = i32
     lib.spx_cc_fit_stack.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64 * 5),
                                      i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    lib.spx_cc_fit_ragged.restype = i32
+    lib.spx_cc_fit_ragged.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32,
+                                      vp, vp, vp, vp, vp, vp, sz, vp]
     lib.spx_cc_fit_frames.restype = i32
     lib.spx_cc_fit_frames.argtypes = [C.POINTER(vp * 5), i32, i32, i64, vp,
                                       i32, i32, i32, i32, u32,

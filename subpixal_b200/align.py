@@ -23,7 +23,7 @@ import torch
 
 from . import batch
 
-__all__ = ["find_linear_fit", "iter_linear_fit", "batched_displacements"]
+__all__ = ["find_linear_fit", "iter_linear_fit", "batched_displacements", "ragged_displacements"]
 
 # attribute names astropy.wcs.WCS uses for non-linear distortions (align.py:36-43)
 _WCS_DISTORTIONS = ("cpdis1", "cpdis2", "det2im1", "det2im2", "sip")
@@ -131,54 +131,62 @@ def iter_linear_fit(xy, uv, wxy=None, wuv=None, fitgeom="general", center=None,
 # --------------------------------------------------------------------------
 # batched displacement + the reference-signature wrapper
 # --------------------------------------------------------------------------
+def ragged_displacements(stack, offsets, shapes, cc_type="NCC", full_output=False):
+    """Displacements of n pairs held on the device as a ragged stack (pair k =
+    ``[5, ny_k, nx_k]`` at ``offsets[k]``; see ``batch.cc_fit_ragged``): at most one
+    launch per size class.  Returns ``(dxdy [n,2] float64, icc list or None)``."""
+    shapes = np.asarray(shapes, dtype=np.int64).reshape(-1, 2)
+    sh, _, _, icc, icc_off = batch.cc_fit_ragged(stack, offsets, shapes, cc_type,
+                                                 want_icc=full_output)
+    dxdy = sh.cpu().numpy()
+    iccs = None
+    if full_output:
+        flat = icc.cpu().numpy()
+        iccs = [flat[int(icc_off[k]):int(icc_off[k + 1])].reshape(2 * shapes[k, 0], 2 * shapes[k, 1])
+                for k in range(shapes.shape[0])]
+    return dxdy, iccs
+
+
+def fill_ref_slots(stack, offsets, shapes, images):
+    """Copy the host image cutouts into slot 0 of their pairs of a ragged device
+    stack: one upload of the concatenated cutouts and one vectorised scatter."""
+    n = len(images)
+    if n == 0:
+        return
+    shapes = np.asarray(shapes, dtype=np.int64).reshape(-1, 2)
+    for k, im in enumerate(images):
+        if tuple(np.shape(im)) != (int(shapes[k, 0]), int(shapes[k, 1])):
+            raise ValueError("All cutouts must have same shape.")            # cc.py:103-105
+    tiles = torch.as_tensor(shapes[:, 0] * shapes[:, 1])
+    compact = np.concatenate([np.ascontiguousarray(im, dtype=np.float32).ravel() for im in images])
+    start = torch.zeros(n, dtype=torch.int64)
+    torch.cumsum(tiles[:-1], 0, out=start[1:])
+    delta = (torch.as_tensor(np.asarray(offsets, dtype=np.int64)) - start).to(stack.device)
+    idx = torch.repeat_interleave(delta, tiles.to(stack.device)) + \
+        torch.arange(int(tiles.sum()), device=stack.device)
+    stack[idx] = torch.from_numpy(compact).to(stack.device)
+
+
 def batched_displacements(stacks, cc_type="NCC", full_output=False):
     """``stacks``: sequence of ``(ref_image, image00, image10, image01, image11)``
-    tuples (numpy, shapes may differ between sources) or ``(ref_image, phases)``
-    pairs where ``phases`` is a CUDA float32 tensor ``[4, ny, nx]`` (the output of
-    ``blot.blot_phases``: the blots never leave the device).  Sources are grouped
-    by shape, every group is one ``spx_cc_fit_stack`` launch.  Returns
-    ``(dxdy [n,2] float64, icc list or None)`` in input order (cc.py:21-95 per
-    source)."""
+    tuples (numpy; shapes may differ between sources, cutout.py:159-175).  The
+    cutouts are packed into one ragged device stack and processed with at most one
+    ``spx_cc_fit_ragged`` launch per size class.  Returns ``(dxdy [n,2] float64,
+    icc list or None)`` in input order (cc.py:21-95 per source)."""
     batch.require_cuda()
     n = len(stacks)
-    dxdy = np.empty((n, 2), dtype=np.float64)
-    iccs = [None] * n if full_output else None
-    groups = {}
+    shapes = np.empty((n, 2), dtype=np.int64)
+    chunks = []
     for k, st in enumerate(stacks):
         shp = tuple(np.shape(st[0]))
-        if len(st) == 2:
-            if tuple(st[1].shape) != (4,) + shp:
-                raise ValueError("All cutouts must have same shape.")
-        elif any(tuple(np.shape(a)) != shp for a in st[1:]):
-            raise ValueError("All cutouts must have same shape.")       # cc.py:103-105
-        groups.setdefault(shp, []).append(k)
-    for shp, idx in groups.items():
-        on_device = [len(stacks[k]) == 2 for k in idx]
-        if all(on_device):
-            refs = np.empty((len(idx),) + shp, dtype=np.float32)
-            for j, k in enumerate(idx):
-                refs[j] = stacks[k][0]
-            dev = stacks[idx[0]][1].device
-            stack = torch.empty((len(idx), 5) + shp, dtype=torch.float32, device=dev)
-            stack[:, 0] = torch.from_numpy(refs).to(dev)
-            for j, k in enumerate(idx):
-                stack[j, 1:] = stacks[k][1]
-        else:
-            host = np.empty((len(idx), 5) + shp, dtype=np.float32)
-            for j, k in enumerate(idx):
-                st = stacks[k]
-                if len(st) == 2:
-                    st = (st[0],) + tuple(st[1].cpu().numpy())
-                for s in range(5):
-                    host[j, s] = st[s]
-            stack = torch.from_numpy(host).cuda()
-        sh, _, _, icc = batch.cc_fit_stack(stack, cc_type, want_icc=full_output)
-        dxdy[idx] = sh.cpu().numpy()
-        if full_output:
-            icc = icc.cpu().numpy()
-            for j, k in enumerate(idx):
-                iccs[k] = icc[j]
-    return dxdy, iccs
+        if len(shp) != 2 or any(tuple(np.shape(a)) != shp for a in st[1:]):
+            raise ValueError("All cutouts must have same shape.")           # cc.py:103-105
+        shapes[k] = shp
+        chunks.extend(np.ascontiguousarray(a, dtype=np.float32).ravel() for a in st)
+    offsets = np.concatenate([[0], np.cumsum(5 * shapes[:, 0] * shapes[:, 1])]).astype(np.int64)
+    flat = np.concatenate(chunks) if n else np.zeros(0, np.float32)
+    return ragged_displacements(torch.from_numpy(flat).cuda(), offsets[:-1], shapes, cc_type,
+                                full_output)
 
 
 def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
@@ -210,11 +218,13 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
         from . import blot as gpu_blot
         for dzct in drz_cutouts:
             dzct.data[dzct.mask] = 0                                   # align.py:661
-        phases = gpu_blot.blot_phases(drz_cutouts, img_cutouts)
-        for imct, ph in zip(img_cutouts, phases):
-            stacks.append((imct.data, ph))
+        dstack, doff, dshp = gpu_blot.blot_phases(drz_cutouts, img_cutouts, as_stack=True)
+        fill_ref_slots(dstack, doff, dshp, [imct.data for imct in img_cutouts])
+        host = dstack.cpu().numpy()
+        for k, imct in enumerate(img_cutouts):
+            tile = int(dshp[k, 0] * dshp[k, 1])
             blt00 = copy.deepcopy(imct)                                # blot.py:152-155
-            blt00.data[:, :] = ph[0].cpu().numpy()
+            blt00.data[:, :] = host[doff[k] + tile:doff[k] + 2 * tile].reshape(dshp[k])
             nonshifted.append(blt00)
     for imct, dzct in (() if blot is None else zip(img_cutouts, drz_cutouts)):
         dx0, dy0 = imct.dx, imct.dy
@@ -231,7 +241,10 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
         nonshifted.append(blt00)
 
     # ---- pass 2 (GPU): every displacement in one batch ------------------------
-    img_dxy, interlaced_cc = batched_displacements(stacks, cc_type, full_output=True)
+    if blot is None:
+        img_dxy, interlaced_cc = ragged_displacements(dstack, doff, dshp, cc_type, full_output=True)
+    else:
+        img_dxy, interlaced_cc = batched_displacements(stacks, cc_type, full_output=True)
 
     # ---- pass 3 (host / WCS): displacement -> tangent-plane coordinates -------
     npts = len(img_cutouts)

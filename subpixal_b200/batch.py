@@ -91,6 +91,64 @@ def cc_fit_stack(stack, cc_type="NCC", want_icc=False):
     return shifts, peak, status, icc
 
 
+_SIZE_CLASSES = (32, 64, 128, 256)
+
+
+def cc_fit_ragged(stack, offsets, shapes, cc_type="NCC", want_icc=False):
+    """Cross-correlate + fit n pairs of DIFFERENT shapes: pair p is the contiguous
+    block ``[5, ny_p, nx_p]`` at element ``offsets[p]`` of the flat float32 CUDA
+    tensor ``stack``, ``shapes[p] = (ny_p, nx_p)`` (ragged cutouts of
+    create_cutouts, reference cutout.py:159-175; cc.py:21-95 per pair).  Pairs are
+    bucketed by size class (32/64/128/256 px) - one launch per class.  Returns
+    ``(shifts [n,2] f64, peak [n] i32, status [n] i32, icc, icc_offsets)`` with
+    ``icc`` a flat float32 tensor holding surface p (``[2ny_p, 2nx_p]``) at
+    ``icc_offsets[p]`` (both None unless ``want_icc``)."""
+    require_cuda()
+    lib = L.load()
+    stack = _f32c(stack, "stack").reshape(-1)
+    dev = stack.device
+    off = torch.as_tensor(offsets).to(dtype=torch.int64, device="cpu").reshape(-1)
+    shp = torch.as_tensor(shapes).to(dtype=torch.int32, device="cpu").reshape(-1, 2)
+    n = int(shp.shape[0])
+    if off.numel() != n:
+        raise ValueError("offsets and shapes must describe the same number of pairs")
+    big = shp.max(dim=1).values if n else shp.new_zeros(0)
+    if n and (int(shp.min()) < L.MIN_CUTOUT or int(big.max()) > L.MAX_CUTOUT):
+        raise L.SubpixalError("subpixal_b200: cutouts must be between %d and %d pixels per axis"
+                              % (L.MIN_CUTOUT, L.MAX_CUTOUT))
+    if n and int((off + 5 * shp[:, 0].long() * shp[:, 1].long()).max()) > stack.numel():
+        raise ValueError("pairs exceed the stack buffer")
+    with torch.cuda.device(dev):
+        shifts = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        peak = torch.empty((n,), dtype=torch.int32, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+        icc = icc_off = d_icc_off = None
+        if want_icc:
+            icc_off = torch.zeros(n + 1, dtype=torch.int64)
+            torch.cumsum(4 * shp[:, 0].long() * shp[:, 1].long(), 0, out=icc_off[1:])
+            icc = torch.empty(int(icc_off[-1]), dtype=torch.float32, device=dev)
+            d_icc_off = icc_off[:-1].contiguous().to(dev)
+        if n == 0:
+            return shifts, peak, status, icc, icc_off
+        d_off, d_shp = off.to(dev), shp.contiguous().to(dev)
+        lo = 0
+        for cls in _SIZE_CLASSES:
+            idx = torch.nonzero((big > lo) & (big <= cls)).reshape(-1)
+            lo = cls
+            m = int(idx.numel())
+            if m == 0:
+                continue
+            my, mx = int(shp[idx, 0].max()), int(shp[idx, 1].max())
+            nb = lib.spx_cc_workspace_bytes(m, my, mx, int(want_icc))
+            ws = _workspace(nb, dev)
+            order = idx.to(torch.int32).to(dev)
+            L.check(lib.spx_cc_fit_ragged(
+                _ptr(stack), _ptr(d_off), _ptr(d_shp), _ptr(order), m, my, mx,
+                cc_type_code(cc_type), _ptr(shifts), _ptr(peak), _ptr(status),
+                _ptr(icc), _ptr(d_icc_off), _ptr(ws), ws.numel(), _stream()))
+    return shifts, peak, status, icc, icc_off
+
+
 def cc_fit_frames(frames, boxes, ny, nx, cc_type="NCC", want_icc=False,
                   zero_bad_phases=True, zero_bad_ref=False):
     """Fused gather + cross-correlation + fit straight from five full frames
@@ -217,7 +275,8 @@ PHASES_00_10_01_11 = ((0.0, 0.0), (0.5, 0.0), (0.0, 0.5), (0.5, 0.5))
 
 
 def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00_10_01_11,
-                scale=None, interp="poly5", misval=0.0, prepare=True):
+                scale=None, interp="poly5", misval=0.0, prepare=True, out=None,
+                out_offsets=None):
     """Batched blot (reference blot.py:79-155 through cdriz.tblot; the four
     half-pixel phases of align.py:661-679 in one launch).
 
@@ -228,7 +287,10 @@ def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00
     Returns ``(out, out_offsets)``: flat float32 tensor holding ``[nph, ny, nx]``
     per cutout and the int64 ``[n+1]`` offsets (CPU).  ``prepare``: (poly5) tabulate
     the sources' x-direction central differences once in a scratch buffer shared by
-    all phases (16 B per source pixel; bit-identical results, about twice as fast)."""
+    all phases (16 B per source pixel; bit-identical results, about twice as fast).
+    ``out`` / ``out_offsets``: write into an existing flat float32 CUDA tensor, phase 0
+    of cutout k at element ``out_offsets[k]`` (e.g. slots 1..4 of a ragged
+    ``cc_fit_ragged`` stack) instead of allocating."""
     require_cuda()
     lib = L.load()
     if interp not in _BLOT_INTERP:
@@ -254,14 +316,24 @@ def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00
     if n and int((s_off + s_shp[:, 0].long() * s_shp[:, 1].long()).max()) > src.numel():
         raise ValueError("source cutouts exceed the src buffer")
     sizes = t_shp[:, 0].long() * t_shp[:, 1].long() * nph
-    o_off = torch.zeros(n + 1, dtype=torch.int64)
-    torch.cumsum(sizes, 0, out=o_off[1:])
+    if out is None:
+        o_off = torch.zeros(n + 1, dtype=torch.int64)
+        torch.cumsum(sizes, 0, out=o_off[1:])
+        o_start = o_off[:-1].contiguous()
+    else:
+        out = _f32c(out, "out")
+        if out.device != dev or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 tensor on the device of src")
+        o_off = o_start = cpu(out_offsets, torch.int64).reshape(-1)
+        if o_start.numel() != n or (n and (int(o_start.min()) < 0 or
+                                           int((o_start + sizes).max()) > out.numel())):
+            raise ValueError("out_offsets must place every blot inside out")
     with torch.cuda.device(dev):
-        out = torch.empty(int(o_off[-1]), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(int(o_off[-1]), dtype=torch.float32, device=dev)
         if n == 0:
             return out, o_off
-        keep = [s_off.to(dev), s_shp.to(dev), mp.to(dev), t_shp.to(dev),
-                o_off[:-1].contiguous().to(dev)]
+        keep = [s_off.to(dev), s_shp.to(dev), mp.to(dev), t_shp.to(dev), o_start.to(dev)]
         d_scale = None
         if scale is not None:
             d_scale = cpu(scale, torch.float32).reshape(-1)

@@ -106,11 +106,15 @@ def _flux_scale(source_cutout, target_cutout, pix_ratio):
 
 
 def blot_phases(source_cutouts, target_cutouts, phases=batch.PHASES_00_10_01_11,
-                interp='poly5', wcsmaps=None, pix_ratios=None, device=None):
+                interp='poly5', wcsmaps=None, pix_ratios=None, device=None, as_stack=False):
     """Blot every source cutout onto its target cutout's grid at all ``phases``
     in one launch.  Returns a list of float32 CUDA tensors ``[nph, ny, nx]`` (views
     into one buffer), one per pair.  ``wcsmaps`` / ``pix_ratios``: optional
-    per-pair overrides (callables like ``BlotWCSMap`` / floats)."""
+    per-pair overrides (callables like ``BlotWCSMap`` / floats).
+
+    ``as_stack=True`` (four phases): returns ``(stack, offsets, shapes)`` laid out
+    for ``batch.cc_fit_ragged`` - pair k is ``[5, ny, nx]`` at ``offsets[k]`` with the
+    blots in slots 1..4 and slot 0 (``ref_image``) left for the caller to fill."""
     batch.require_cuda()
     source_cutouts, target_cutouts = list(source_cutouts), list(target_cutouts)
     n = len(source_cutouts)
@@ -138,11 +142,22 @@ def blot_phases(source_cutouts, target_cutouts, phases=batch.PHASES_00_10_01_11,
     sizes = s_shp[:, 0] * s_shp[:, 1]
     s_off = np.concatenate([[0], np.cumsum(sizes)]) if n else np.zeros(1, np.int64)
     flat = np.concatenate(chunks) if n else np.zeros(0, np.float32)
+    nph = len(tuple(phases))
+    if as_stack:
+        if nph != 4:
+            raise ValueError("as_stack needs the four phases of find_displacement")
+        tiles = t_shp[:, 0] * t_shp[:, 1]
+        p_off = np.concatenate([[0], np.cumsum(5 * tiles)]).astype(np.int64)
+        with torch.cuda.device(dev):
+            stack = torch.empty(int(p_off[-1]), dtype=torch.float32, device=dev)
+            src = torch.from_numpy(flat).to(dev)
+            batch.blot_phases(src, s_off[:-1], s_shp, maps, t_shp, phases=phases, scale=scale,
+                              interp=interp, misval=0.0, out=stack, out_offsets=p_off[:-1] + tiles)
+        return stack, p_off[:-1], t_shp
     with torch.cuda.device(dev):
         src = torch.from_numpy(flat).to(dev)
         out, o_off = batch.blot_phases(src, s_off[:-1], s_shp, maps, t_shp, phases=phases,
                                        scale=scale, interp=interp, misval=0.0)
-    nph = len(tuple(phases))
     res = []
     for k in range(n):
         ny, nx = int(t_shp[k, 0]), int(t_shp[k, 1])

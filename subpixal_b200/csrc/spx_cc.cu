@@ -22,6 +22,9 @@ struct CcParams {
     long long pitch;            // row pitch of every source (elements)
     int H, W;                   // source image size
     const int *boxes;           // [n,4] or nullptr (stack mode)
+    // ragged mode (shapes != nullptr): pair p = order[k] has shape shapes[p], its five
+    // tiles [5][ny][nx] start at src[0] + offsets[p]; ny/nx below are the largest shape
+    const int *shapes; const long long *offsets; const int *order; const long long *icc_offsets;
     int n, ny, nx, cc_type;
     unsigned flags;
     double *shifts; int *peak; int *status; float *icc_out;
@@ -199,8 +202,18 @@ __device__ __forceinline__ PfMap prefetch_map(int nx, int lane) {
     return m;
 }
 template <class C>
-__device__ __forceinline__ void prefetch_pair(const CcParams &prm, int p, const PfMap &m) {
-    if (p >= prm.n) return;
+__device__ __forceinline__ void prefetch_pair(const CcParams &prm, int k, const PfMap &m) {
+    if (k >= prm.n) return;
+    if (prm.shapes) {                        // ragged stack: the pair is one contiguous block
+        const int p = prm.order ? __ldg(prm.order + k) : k;
+        const long long elems = 5LL * __ldg(prm.shapes + 2 * p) * __ldg(prm.shapes + 2 * p + 1);
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(prm.src[0] + __ldg(prm.offsets + p));
+        const uintptr_t hi = lo + 4 * elems;
+        for (uintptr_t line = (lo & ~uintptr_t(127)) + 128 * threadIdx.x; line < hi; line += 128 * C::T)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+        return;
+    }
+    const int p = k;
     int x1 = 0, y1 = 0;
     if (prm.boxes) {
         const int4 b = __ldg(reinterpret_cast<const int4 *>(prm.boxes) + p);
@@ -278,22 +291,40 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
 
     const size_t icc_elems = size_t(4) * prm.ny * prm.nx;
     const PfMap pfmap = prefetch_map(prm.nx, threadIdx.x & 31);
-    for (int p = unit; p < prm.n; p += nunits) {
-        c.icc = prm.icc_out ? prm.icc_out + size_t(p) * icc_elems
-                            : reinterpret_cast<float *>(slab + prm.off_icc);
+    for (int k = unit; k < prm.n; k += nunits) {
+        const int p = prm.order ? __ldg(prm.order + k) : k;
         PairJob job;
         job.x1 = 0; job.y1 = 0; job.status0 = 0;
-        if (prm.boxes) {
-            const int4 b = __ldg(reinterpret_cast<const int4 *>(prm.boxes) + p);
-            job.x1 = b.x; job.y1 = b.y;
-            if (b.z - b.x + 1 != prm.nx || b.w - b.y + 1 != prm.ny)
-                job.status0 = SPX_S_BOX_MISMATCH;
-        }
-        for (int s = 0; s < 5; ++s) job.base[s] = prm.src[s] + size_t(p) * prm.pair_stride[s];
+        job.ny = prm.ny; job.nx = prm.nx;
         job.pitch = prm.pitch; job.H = prm.H; job.W = prm.W;
-        job.ny = prm.ny; job.nx = prm.nx; job.cc_type = prm.cc_type;
+        size_t icc_off = size_t(p) * icc_elems;
+        if (prm.shapes) {
+            job.ny = __ldg(prm.shapes + 2 * p); job.nx = __ldg(prm.shapes + 2 * p + 1);
+            // a shape outside this launch's size class cannot be processed: flag it and
+            // run a minimal pair instead (the host buckets by class, so this is a caller bug)
+            if (job.ny < SPX_MIN_CUTOUT || job.nx < SPX_MIN_CUTOUT || job.ny > C::NMAX || job.nx > C::NMAX) {
+                job.status0 = SPX_S_BOX_MISMATCH;
+                job.ny = job.nx = SPX_MIN_CUTOUT;
+            }
+            const size_t tile = size_t(job.ny) * job.nx;
+            const float *b0 = prm.src[0] + __ldg(prm.offsets + p);
+            for (int s = 0; s < 5; ++s) job.base[s] = b0 + s * tile;
+            job.pitch = job.nx; job.H = job.ny; job.W = job.nx;
+            if (prm.icc_offsets) icc_off = size_t(__ldg(prm.icc_offsets + p));
+        } else {
+            if (prm.boxes) {
+                const int4 b = __ldg(reinterpret_cast<const int4 *>(prm.boxes) + p);
+                job.x1 = b.x; job.y1 = b.y;
+                if (b.z - b.x + 1 != prm.nx || b.w - b.y + 1 != prm.ny)
+                    job.status0 = SPX_S_BOX_MISMATCH;
+            }
+            for (int s = 0; s < 5; ++s) job.base[s] = prm.src[s] + size_t(p) * prm.pair_stride[s];
+        }
+        c.icc = prm.icc_out ? prm.icc_out + icc_off
+                            : reinterpret_cast<float *>(slab + prm.off_icc);
+        job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
-        if (rank == 0) prefetch_pair<C>(prm, p + nunits, pfmap);
+        if (rank == 0) prefetch_pair<C>(prm, k + nunits, pfmap);
         process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
     }
     if (C::CL == 2) cg::this_cluster().sync();     // do not exit while the peer may still read my W
@@ -423,6 +454,23 @@ int spx_cc_fit_stack(const float *ref, const float *im00, const float *im10,
     prm.pitch = nx; prm.H = ny; prm.W = nx;
     prm.boxes = nullptr;
     prm.n = n; prm.ny = ny; prm.nx = nx; prm.cc_type = cc_type; prm.flags = 0;
+    prm.shifts = shifts; prm.peak = peak; prm.status = status; prm.icc_out = icc;
+    return spx::run_cc(prm, workspace, workspace_bytes, stream);
+}
+
+int spx_cc_fit_ragged(const float *stack, const int64_t *offsets, const int32_t *shapes,
+                      const int32_t *order, int n, int max_ny, int max_nx, int cc_type,
+                      double *shifts, int32_t *peak, int32_t *status,
+                      float *icc, const int64_t *icc_offsets,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+    if (!stack || !offsets || !shapes || (icc && !icc_offsets)) return SPX_E_BADARG;
+    spx::CcParams prm{};
+    for (int s = 0; s < 5; ++s) { prm.src[s] = stack; prm.pair_stride[s] = 0; }
+    prm.pitch = max_nx; prm.H = max_ny; prm.W = max_nx;
+    prm.boxes = nullptr;
+    prm.shapes = shapes; prm.offsets = reinterpret_cast<const long long *>(offsets);
+    prm.order = order; prm.icc_offsets = reinterpret_cast<const long long *>(icc_offsets);
+    prm.n = n; prm.ny = max_ny; prm.nx = max_nx; prm.cc_type = cc_type; prm.flags = 0;
     prm.shifts = shifts; prm.peak = peak; prm.status = status; prm.icc_out = icc;
     return spx::run_cc(prm, workspace, workspace_bytes, stream);
 }

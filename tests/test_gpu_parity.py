@@ -329,3 +329,39 @@ def test_randomised_shapes_masks_and_nans():
                 assert (srt[-1] - srt[-2]) <= 1e-5 * abs(srt[-1]), tag
                 continue
             assert abs(sh[k, 0] - dx) < 1e-4 and abs(sh[k, 1] - dy) < 1e-4, tag
+
+
+def test_ragged_stack_matches_uniform_launches_and_oracle():
+    """spx_cc_fit_ragged: pairs of different shapes in one table, one launch per
+    size class; every pair must equal what a uniform spx_cc_fit_stack launch gives
+    (same kernel, same job) and agree with the oracle."""
+    from subpixal_b200 import batch
+    import subpixal_b200._lib as L
+    shapes = [(3, 5), (20, 37), (32, 32), (33, 40), (64, 64), (64, 64), (17, 64), (100, 90),
+              (128, 128), (130, 200), (256, 256), (6, 6), (48, 48), (64, 64)]
+    pairs = [orc.random_pairs(1, ny, nx, seed=900 + k, masked=(k % 3 == 0))[0][0]
+             for k, (ny, nx) in enumerate(shapes)]
+    sizes = np.array([5 * ny * nx for ny, nx in shapes])
+    offsets = np.concatenate([[0], np.cumsum(sizes)])[:-1]
+    flat = torch.from_numpy(np.concatenate([p.ravel() for p in pairs]).astype(np.float32)).cuda()
+    for t in ("NCC", "ZNCC"):
+        sh, pk, st, icc, ioff = batch.cc_fit_ragged(flat, offsets, shapes, t, want_icc=True)
+        sh2, pk2, st2, _, _ = batch.cc_fit_ragged(flat, offsets, shapes, t)
+        assert torch.equal(sh, sh2) and torch.equal(pk, pk2) and torch.equal(st, st2)
+        sh, pk, st, icc = sh.cpu().numpy(), pk.cpu().numpy(), st.cpu().numpy(), icc.cpu().numpy()
+        for k, (ny, nx) in enumerate(shapes):
+            u = batch.cc_fit_stack(torch.from_numpy(pairs[k][None]).cuda(), t, want_icc=True)
+            assert np.array_equal(u[0].cpu().numpy()[0], sh[k]) and int(u[1][0]) == pk[k]
+            got_icc = icc[ioff[k]:ioff[k + 1]].reshape(2 * ny, 2 * nx)
+            assert np.array_equal(u[3].cpu().numpy()[0], got_icc)
+            dx, dy, ricc, _ = _oracle(pairs[k], t)
+            assert abs(sh[k, 0] - dx) < 5e-5 and abs(sh[k, 1] - dy) < 5e-5, (k, t)
+            assert pk[k] == int(np.argmax(ricc)) and st[k] == int(u[2][0])
+            assert _rel_l2(got_icc, ricc) < ICC_L2_TOL
+    # empty table, and shapes the kernels do not support
+    e = batch.cc_fit_ragged(flat[:0], [], np.zeros((0, 2), int))
+    assert e[0].shape == (0, 2) and e[3] is None
+    with pytest.raises(L.SubpixalError):
+        batch.cc_fit_ragged(flat, [0], [(2, 8)])
+    with pytest.raises(L.SubpixalError):
+        batch.cc_fit_ragged(flat, [0], [(8, 257)])

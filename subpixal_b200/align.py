@@ -23,7 +23,8 @@ import torch
 
 from . import batch
 
-__all__ = ["find_linear_fit", "iter_linear_fit", "batched_displacements", "ragged_displacements"]
+__all__ = ["find_linear_fit", "iter_linear_fit", "batched_displacements", "ragged_displacements",
+           "frame_displacements"]
 
 # attribute names astropy.wcs.WCS uses for non-linear distortions (align.py:36-43)
 _WCS_DISTORTIONS = ("cpdis1", "cpdis2", "det2im1", "det2im2", "sip")
@@ -187,6 +188,163 @@ def batched_displacements(stacks, cc_type="NCC", full_output=False):
     flat = np.concatenate(chunks) if n else np.zeros(0, np.float32)
     return ragged_displacements(torch.from_numpy(flat).cuda(), offsets[:-1], shapes, cc_type,
                                 full_output)
+
+
+class _Tables(object):
+    """Packs the per-source tables of one ``frame_displacements`` call into ONE pinned
+    host buffer and uploads it with a single asynchronous copy, so the host never
+    waits for the device between the five launches of the pipeline."""
+
+    def __init__(self):
+        self.parts, self.size = [], 0
+
+    def add(self, arr, dtype):
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        off = self.size
+        self.parts.append((off, arr))
+        self.size = (off + arr.nbytes + 15) // 16 * 16
+        return off
+
+    def upload(self, dev):
+        host = torch.empty(max(self.size, 16), dtype=torch.uint8, pin_memory=True)
+        view = host.numpy()
+        for off, arr in self.parts:
+            view[off:off + arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        self.dev = host.to(dev, non_blocking=True)
+        self.base = self.dev.data_ptr()
+        return self
+
+    def ptr(self, off):
+        return self.base + off
+
+
+def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, flux_scale=1.0,
+                        cc_type="NCC", drz_seg=None, src_ids=None, interp="poly5",
+                        full_output=False, maps=None):
+    """The measurement half of ``_align_1image`` (align.py:464-560 -> 561-699) for one
+    image, entirely on the device: crop the image cutouts (``img_boxes``) and the
+    drizzled cutouts (``drz_boxes``; pixels of other segments zeroed when ``drz_seg``
+    and ``src_ids`` are given, cutout.py:416-427 + align.py:661), blot every drizzled
+    cutout onto its image cutout's grid at the four half-pixel phases
+    (align.py:664-679), cross-correlate and fit (cc.py:21-95).
+
+    ``img_frame`` / ``drz_frame``: 2-D float32 CUDA tensors; boxes ``[n, 4]``
+    (x1, y1, x2, y2), trc inclusive, sizes may differ between sources;
+    ``frame_map(x, y)``: vectorised map from 0-based image-frame pixels to 0-based
+    drizzled-frame pixels (the WCS composition of blot.py:21-76), sampled at 9 points
+    per source - or pass ``maps`` (``[n, 20]``, from ``blot.fit_pixel_maps``) computed
+    earlier and ``frame_map=None``;
+    ``flux_scale``: scalar or ``[n]`` (``ef / pix_ratio**2`` and unit conversions).
+    Returns ``(shifts [n,2] f64, peak [n] i32, status [n] i32)`` CUDA tensors, plus
+    ``(icc, icc_offsets)`` when ``full_output``.  The per-source tables travel in one
+    asynchronous upload; the launches (2 gathers, blot preparation, blot, one CC+fit
+    per size class) are only enqueued - nothing here waits for the device."""
+    import ctypes as C
+    from . import _lib as L
+    from . import blot as gpu_blot
+    batch.require_cuda()
+    lib = L.load()
+    ib = np.asarray(img_boxes, dtype=np.int64).reshape(-1, 4)
+    db = np.asarray(drz_boxes, dtype=np.int64).reshape(-1, 4)
+    n = ib.shape[0]
+    if db.shape[0] != n:
+        raise ValueError("The number of image cutouts must match the number "
+                         "of drizzled cutouts.")
+    if interp not in batch._BLOT_INTERP:
+        raise ValueError("interp %r is not supported on the GPU (nearest, linear, poly5)" % (interp,))
+    for name, fr in (("img_frame", img_frame), ("drz_frame", drz_frame)):
+        if not (fr.is_cuda and fr.dim() == 2 and fr.dtype == torch.float32 and fr.stride(1) == 1):
+            raise ValueError(name + " must be a 2-D float32 CUDA tensor with unit column stride")
+    dev = img_frame.device
+    t_shp = np.stack([ib[:, 3] - ib[:, 1] + 1, ib[:, 2] - ib[:, 0] + 1], axis=1)
+    s_shp = np.stack([db[:, 3] - db[:, 1] + 1, db[:, 2] - db[:, 0] + 1], axis=1)
+    if n and (t_shp.min() < 1 or s_shp.min() < 1):
+        raise ValueError("Ill-formed extraction box")
+    big = t_shp.max(axis=1) if n else np.zeros(0, np.int64)
+    if n and (t_shp.min() < L.MIN_CUTOUT or big.max() > L.MAX_CUTOUT):
+        raise L.SubpixalError("subpixal_b200: cutouts must be between %d and %d pixels per axis"
+                              % (L.MIN_CUTOUT, L.MAX_CUTOUT))
+    tiles = t_shp[:, 0] * t_shp[:, 1]
+    p_off = np.concatenate([[0], np.cumsum(5 * tiles)]).astype(np.int64)
+    s_off = np.concatenate([[0], np.cumsum(s_shp[:, 0] * s_shp[:, 1])]).astype(np.int64)
+    w_units = (s_shp[:, 0] + 5) * (s_shp[:, 1] + 1)               # spx_blot_workspace_bytes / 16
+    w_off = np.concatenate([[0], np.cumsum(w_units)]).astype(np.int64)
+    i_off = np.concatenate([[0], np.cumsum(4 * tiles)]).astype(np.int64)
+    with torch.cuda.device(dev):
+        shifts = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        peak = torch.empty((n,), dtype=torch.int32, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+        icc = torch.empty(int(i_off[-1]), dtype=torch.float32, device=dev) if full_output else None
+        if n == 0:
+            return (shifts, peak, status, icc, i_off) if full_output else (shifts, peak, status)
+        stack = torch.empty(int(p_off[-1]), dtype=torch.float32, device=dev)
+        src = torch.empty(int(s_off[-1]), dtype=torch.float32, device=dev)
+        prepared = interp == "poly5"
+        bws = torch.empty(int(w_off[-1]) * 4 if prepared else 4, dtype=torch.float32, device=dev)
+        # ---- every table, one upload -------------------------------------------------
+        T = _Tables()
+        o_ib, o_db = T.add(ib, np.int32), T.add(db, np.int32)
+        o_poff, o_soff = T.add(p_off[:-1], np.int64), T.add(s_off[:-1], np.int64)
+        o_boff = T.add(p_off[:-1] + tiles, np.int64)
+        o_sshp, o_tshp = T.add(s_shp, np.int32), T.add(t_shp, np.int32)
+        if maps is None:
+            maps = gpu_blot.fit_pixel_maps(frame_map, ib, db)
+        if np.shape(maps) != (n, 20):
+            raise ValueError("maps must have shape [n, 20]")
+        o_map = T.add(maps, np.float64)
+        o_scale = T.add(np.broadcast_to(np.asarray(flux_scale, dtype=np.float32), (n,)), np.float32)
+        o_woff, o_ioff = T.add(w_off[:-1], np.int64), T.add(i_off[:-1], np.int64)
+        use_seg = drz_seg is not None and src_ids is not None
+        o_ids = T.add(np.asarray(src_ids).reshape(-1), np.int64) if use_seg else 0
+        classes, lo = [], 0
+        for cls in batch._SIZE_CLASSES:
+            idx = np.flatnonzero((big > lo) & (big <= cls))
+            lo = cls
+            if idx.size:
+                classes.append((T.add(idx, np.int32), idx.size, int(t_shp[idx, 0].max()),
+                                int(t_shp[idx, 1].max())))
+        T.upload(dev)
+        st = batch._stream()
+        # ---- image cutouts -> slot 0 of the ragged stack; drizzled cutouts -> blot sources
+        for frame, o_box, o_off, out, hw, zero, seg in (
+                (img_frame, o_ib, o_poff, stack, t_shp, 0, None),
+                (drz_frame, o_db, o_soff, src, s_shp, 1, drz_seg if use_seg else None)):
+            a = L.GatherArgs()
+            a.frame, a.frame_kind = frame.data_ptr(), L.T_F32
+            a.frame_h, a.frame_w, a.frame_pitch = int(frame.shape[0]), int(frame.shape[1]), int(frame.stride(0))
+            if seg is not None:
+                if tuple(seg.shape) != tuple(frame.shape) or seg.dtype not in (torch.int32, torch.int64):
+                    raise ValueError("segmentation image must be int32/int64 with the frame's shape")
+                seg = seg.contiguous()
+                a.seg, a.seg_kind, a.src_ids = seg.data_ptr(), batch._KIND[seg.dtype], T.ptr(o_ids)
+            a.boxes, a.out_offset, a.n = T.ptr(o_box), T.ptr(o_off), n
+            a.max_h, a.max_w = int(hw[:, 0].max()), int(hw[:, 1].max())
+            a.fillval, a.zero_masked = 0.0, zero
+            a.data_out = out.data_ptr()
+            L.check(lib.spx_gather_cutouts(C.byref(a), st))
+        # ---- blot at the four phases into slots 1..4 ---------------------------------
+        b = L.BlotArgs()
+        b.src, b.src_offset, b.src_shape = src.data_ptr(), T.ptr(o_soff), T.ptr(o_sshp)
+        b.map, b.scale = T.ptr(o_map), T.ptr(o_scale)
+        b.tgt_shape, b.out_offset, b.out = T.ptr(o_tshp), T.ptr(o_boff), stack.data_ptr()
+        ph = (C.c_double * 8)(*[v for p2 in batch.PHASES_00_10_01_11 for v in p2])
+        b.phases_host = C.cast(ph, C.POINTER(C.c_double))
+        b.n, b.nph, b.interp = n, 4, batch._BLOT_INTERP[interp]
+        b.max_ny, b.max_nx, b.misval = int(t_shp[:, 0].max()), int(t_shp[:, 1].max()), 0.0
+        if prepared:
+            b.workspace, b.ws_offset = bws.data_ptr(), T.ptr(o_woff)
+            b.max_src_h, b.max_src_w = int(s_shp[:, 0].max()), int(s_shp[:, 1].max())
+        L.check(lib.spx_blot_phases(C.byref(b), st))
+        # ---- cross-correlation + fit, one launch per size class -----------------------
+        for o_idx, m, my, mx in classes:
+            ws = batch._workspace(lib.spx_cc_workspace_bytes(m, my, mx, int(full_output)), dev)
+            L.check(lib.spx_cc_fit_ragged(
+                C.c_void_p(stack.data_ptr()), C.c_void_p(T.ptr(o_poff)), C.c_void_p(T.ptr(o_tshp)),
+                C.c_void_p(T.ptr(o_idx)), m, my, mx, batch.cc_type_code(cc_type),
+                batch._ptr(shifts), batch._ptr(peak), batch._ptr(status), batch._ptr(icc),
+                C.c_void_p(T.ptr(o_ioff)) if full_output else C.c_void_p(0),
+                batch._ptr(ws), ws.numel(), st))
+    return (shifts, peak, status, icc, i_off) if full_output else (shifts, peak, status)
 
 
 def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',

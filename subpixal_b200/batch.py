@@ -366,6 +366,60 @@ def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00
     return out, o_off
 
 
+def gather_into(frame, boxes, out, out_offsets, fillval=0.0, zero_masked=False, seg=None,
+                src_ids=None, dq=None, dq_good_bits=None):
+    """Crop ``boxes`` ([n,4] x1,y1,x2,y2, trc inclusive) out of the 2-D float32 CUDA
+    ``frame`` straight into the flat float32 tensor ``out``, cutout k at element
+    ``out_offsets[k]`` (``spx_gather_cutouts`` without a mask output): used to place
+    image cutouts in slot 0 of a ragged ``cc_fit_ragged`` stack and to build the
+    source stack of ``blot_phases`` without a host round trip.  Masked pixels
+    (outside the frame, non-finite, ``seg != src_id``, bad DQ bits) are zeroed when
+    ``zero_masked`` (align.py:661)."""
+    require_cuda()
+    lib = L.load()
+    frame = _f32c(frame, "frame")
+    out = _f32c(out, "out")
+    if frame.dim() != 2 or not out.is_contiguous():
+        raise ValueError("frame must be 2-D and out contiguous")
+    dev = frame.device
+    H, W = (int(v) for v in frame.shape)
+    bx = torch.as_tensor(boxes).to(dtype=torch.int64, device="cpu").reshape(-1, 4)
+    n = int(bx.shape[0])
+    if n == 0:
+        return
+    hw = torch.stack([bx[:, 3] - bx[:, 1] + 1, bx[:, 2] - bx[:, 0] + 1], dim=1)
+    off = torch.as_tensor(out_offsets).to(dtype=torch.int64, device="cpu").reshape(-1)
+    if int(hw.min()) < 1:
+        raise ValueError("Ill-formed extraction box")
+    if off.numel() != n or int(off.min()) < 0 or int((off + hw[:, 0] * hw[:, 1]).max()) > out.numel():
+        raise ValueError("out_offsets must place every cutout inside out")
+    with torch.cuda.device(dev):
+        keep = [bx.to(torch.int32).to(dev), off.to(dev)]
+        a = L.GatherArgs()
+        a.frame, a.frame_kind = frame.data_ptr(), L.T_F32
+        a.frame_h, a.frame_w, a.frame_pitch = H, W, int(frame.stride(0))
+        if seg is not None and src_ids is not None:
+            if tuple(seg.shape) != (H, W) or seg.dtype not in (torch.int32, torch.int64):
+                raise ValueError("segmentation image must be int32/int64 with the frame's shape")
+            seg = seg.contiguous()
+            keep.append(torch.as_tensor(src_ids).to(dtype=torch.int64).reshape(-1).to(dev))
+            if keep[-1].numel() != n:
+                raise ValueError("src_ids must have one entry per box")
+            a.seg, a.seg_kind, a.src_ids = seg.data_ptr(), _KIND[seg.dtype], keep[-1].data_ptr()
+        if dq is not None:
+            if tuple(dq.shape) != (H, W) or dq.dtype not in _KIND or dq.is_floating_point():
+                raise ValueError("DQ image must be an integer image with the frame's shape")
+            dq = dq.contiguous()
+            a.dq, a.dq_kind = dq.data_ptr(), _KIND[dq.dtype]
+            a.dq_use_bits = int(dq_good_bits is not None)
+            a.dq_good_bits = int(dq_good_bits) if dq_good_bits is not None else 0
+        a.boxes, a.out_offset, a.n = keep[0].data_ptr(), keep[1].data_ptr(), n
+        a.max_h, a.max_w = int(hw[:, 0].max()), int(hw[:, 1].max())
+        a.fillval, a.zero_masked = float(fillval), int(bool(zero_masked))
+        a.data_out = out.data_ptr()
+        L.check(lib.spx_gather_cutouts(C.byref(a), _stream()))
+
+
 def find_peak_batch(surfaces, mask=None, guess=None, search_box=(0, 0),
                     fit_box=(5, 5)):
     """Batched centroid.find_peak (reference centroid.py:18-236) on a

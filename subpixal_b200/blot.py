@@ -29,7 +29,8 @@ import torch
 
 from . import batch
 
-__all__ = ['BlotWCSMap', 'blot_cutout', 'blot_phases', 'fit_pixel_map', 'pixel_ratio']
+__all__ = ['BlotWCSMap', 'blot_cutout', 'blot_phases', 'fit_pixel_map', 'fit_pixel_maps',
+           'pixel_ratio']
 
 _SUPPORTED = ('nearest', 'linear', 'poly5')
 _DRIZZLE_ONLY = ('poly3', 'spline3', 'sinc', 'lanczos3', 'lanczos5')
@@ -68,6 +69,35 @@ def fit_pixel_map(wcsmap, nx, ny):
     a = diff(diff(xs, hx, 0), hy, 1)
     b = diff(diff(ys, hx, 0), hy, 1)
     return np.concatenate([[xc, yc], a.ravel(), b.ravel()])
+
+
+def fit_pixel_maps(frame_map, target_boxes, source_boxes):
+    """Vectorised ``fit_pixel_map`` for n cutouts of two full frames: ``frame_map(x, y)``
+    maps 0-based pixels of the target (image) frame to 0-based pixels of the source
+    (drizzled) frame and accepts arrays; boxes are ``[n, 4]`` (x1, y1, x2, y2), trc
+    inclusive.  One call of ``frame_map`` with 9n points.  Returns ``[n, 20]``."""
+    tb = np.asarray(target_boxes, dtype=np.float64).reshape(-1, 4)
+    sb = np.asarray(source_boxes, dtype=np.float64).reshape(-1, 4)
+    n = tb.shape[0]
+    xc = 0.5 * (tb[:, 2] - tb[:, 0])
+    yc = 0.5 * (tb[:, 3] - tb[:, 1])
+    hx, hy = np.maximum(xc, 0.5), np.maximum(yc, 0.5)
+    # node (p, q) = (xc + (p-1) hx, yc + (q-1) hy); all arrays are [9, n] with n contiguous
+    px = np.stack([xc + tb[:, 0] + (p - 1) * hx for p in range(3) for q in range(3)])
+    py = np.stack([yc + tb[:, 1] + (q - 1) * hy for p in range(3) for q in range(3)])
+    gx, gy = frame_map(px.ravel(), py.ravel())
+    out = np.empty((n, 20), np.float64)
+    out[:, 0], out[:, 1] = xc, yc
+    for base, g, origin in ((2, gx, sb[:, 0]), (11, gy, sb[:, 1])):
+        f = np.asarray(g, np.float64).reshape(3, 3, n) - origin           # [p, q, n]
+        # coefficients of 1, u, u^2 along p (exact for linear maps), then of 1, v, v^2 along q
+        cu = (f[1], (f[2] - f[0]) / (2.0 * hx), ((f[2] - f[1]) - (f[1] - f[0])) / (2.0 * hx * hx))
+        for p in range(3):
+            c = cu[p]                                                      # [q, n]
+            out[:, base + 3 * p + 0] = c[1]
+            out[:, base + 3 * p + 1] = (c[2] - c[0]) / (2.0 * hy)
+            out[:, base + 3 * p + 2] = ((c[2] - c[1]) - (c[1] - c[0])) / (2.0 * hy * hy)
+    return out
 
 
 def pixel_ratio(source_cutout, target_cutout):

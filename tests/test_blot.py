@@ -245,3 +245,62 @@ def test_gpu_blot_cutout_and_linear_fit_with_device_blot():
     assert np.max(np.abs(np.median(d, axis=0) - (-err))) < 0.02 or \
         np.max(np.abs(np.median(d, axis=0) - err)) < 0.02
     assert np.array_equal(blts[0].data, b.data)
+
+
+@pytest.mark.gpu
+def test_frame_pipeline_matches_the_cutout_object_path():
+    """align.frame_displacements (gather + gather + blot + ragged CC, all on the
+    device) against find_linear_fit over Cutout objects on the same frames."""
+    from subpixal_b200 import align, blot, cutout
+    rng = np.random.default_rng(5)
+    H = W = 360
+    nsrc = 24
+    cx = rng.uniform(45, W - 45, nsrc); cy = rng.uniform(45, H - 45, nsrc)
+    amp = rng.uniform(300, 3000, nsrc); sig = rng.uniform(1.6, 3.2, nsrc)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+
+    def scene(wx, wy):
+        v = np.zeros(np.shape(wx))
+        for k in range(nsrc):
+            v += amp[k] * np.exp(-((wx - cx[k]) ** 2 + (wy - cy[k]) ** 2) / (2 * sig[k] ** 2))
+        return v
+
+    drz = scene(xx, yy).astype(np.float32)
+    th = -1.5e-3
+    m = 0.998 * np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    t = np.array([-1.7, 2.4])
+    wimg = _AffineWcs(m, t)
+    wx, wy = wimg.all_pix2world(xx, yy, 0)
+    img = (scene(wx + 0.2, wy - 0.1) + rng.standard_normal((H, W))).astype(np.float32)
+    wdrz = _AffineWcs()
+    ib, db, imgs, drzs = [], [], [], []
+    for k in range(nsrc):
+        px, py = np.linalg.solve(m, np.array([cx[k], cy[k]]) - t)
+        hw, hh = int(rng.integers(10, 30)), int(rng.integers(10, 30))       # ragged boxes
+        x1, y1 = int(round(px)) - hw, int(round(py)) - hh
+        X1, Y1 = int(round(cx[k])) - hw - 8, int(round(cy[k])) - hh - 8
+        ib.append((x1, y1, x1 + 2 * hw - 1, y1 + 2 * hh - 1))
+        db.append((X1, Y1, X1 + 2 * hw + 15, Y1 + 2 * hh + 15))
+        imgs.append(cutout.Cutout(img, wimg, blc=ib[-1][:2], trc=ib[-1][2:], src_id=k, mode='fill',
+                                  fillval=0.0))
+        drzs.append(cutout.Cutout(drz, wdrz, blc=db[-1][:2], trc=db[-1][2:], src_id=k, mode='fill',
+                                  fillval=0.0))
+    fit, iccs, _ = align.find_linear_fit(imgs, drzs, fitgeom='shift', nclip=0, use_weights=False)
+    want = fit['subpixal_img_dxy']
+
+    def frame_map(x, y):
+        return wdrz.all_world2pix(*wimg.all_pix2world(x, y, 0), 0)
+
+    pr = blot.pixel_ratio(drzs[0], imgs[0])
+    sh, pk, st, icc, ioff = align.frame_displacements(
+        torch.from_numpy(img).cuda(), torch.from_numpy(drz).cuda(), ib, db, frame_map,
+        flux_scale=1.0 / pr ** 2, full_output=True)
+    got = sh.cpu().numpy()
+    assert np.max(np.abs(got - want)) < 1e-5
+    assert np.max(np.abs(np.median(got, axis=0) - np.array([0.2, -0.1]) / 0.998)) < 0.03 or \
+        np.max(np.abs(np.median(got, axis=0) + np.array([0.2, -0.1]) / 0.998)) < 0.03
+    k = 3
+    ny, nx = ib[k][3] - ib[k][1] + 1, ib[k][2] - ib[k][0] + 1
+    g = icc.cpu().numpy()[ioff[k]:ioff[k + 1]].reshape(2 * ny, 2 * nx)
+    assert np.linalg.norm(g - iccs[k]) / np.linalg.norm(iccs[k]) < 1e-5
+    assert int((st.cpu().numpy() != 0).sum()) == 0

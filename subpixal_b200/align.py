@@ -205,12 +205,30 @@ class _Tables(object):
         self.size = (off + arr.nbytes + 15) // 16 * 16
         return off
 
+    # ring of pinned staging buffers (per device): a slot is reused only after the copy
+    # that last read it has completed, so repeated calls neither allocate pinned memory
+    # nor wait for the device unless more than RING uploads are in flight
+    RING = 4
+    _ring = {}
+
     def upload(self, dev):
-        host = torch.empty(max(self.size, 16), dtype=torch.uint8, pin_memory=True)
+        slots = self._ring.setdefault(dev.index, {"next": 0, "bufs": [None] * self.RING})
+        k = slots["next"]
+        slots["next"] = (k + 1) % self.RING
+        entry = slots["bufs"][k]
+        if entry is not None:
+            entry[1].synchronize()
+        if entry is None or entry[0].numel() < self.size:
+            entry = [torch.empty(max(self.size, 1 << 16), dtype=torch.uint8, pin_memory=True), None]
+        host = entry[0]
         view = host.numpy()
         for off, arr in self.parts:
             view[off:off + arr.nbytes] = arr.view(np.uint8).reshape(-1)
-        self.dev = host.to(dev, non_blocking=True)
+        self.dev = torch.empty(max(self.size, 16), dtype=torch.uint8, device=dev)
+        self.dev.copy_(host[:self.dev.numel()], non_blocking=True)
+        entry[1] = torch.cuda.Event()
+        entry[1].record(torch.cuda.current_stream(dev))
+        slots["bufs"][k] = entry
         self.base = self.dev.data_ptr()
         return self
 
@@ -277,10 +295,11 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
         icc = torch.empty(int(i_off[-1]), dtype=torch.float32, device=dev) if full_output else None
         if n == 0:
             return (shifts, peak, status, icc, i_off) if full_output else (shifts, peak, status)
-        stack = torch.empty(int(p_off[-1]), dtype=torch.float32, device=dev)
-        src = torch.empty(int(s_off[-1]), dtype=torch.float32, device=dev)
+        # internal scratch (ragged CC stack, blot sources, prepared sources): reused across calls
+        stack = batch.scratch_f32("fd.stack", int(p_off[-1]), dev)
+        src = batch.scratch_f32("fd.src", int(s_off[-1]), dev)
         prepared = interp == "poly5"
-        bws = torch.empty(int(w_off[-1]) * 4 if prepared else 4, dtype=torch.float32, device=dev)
+        bws = batch.scratch_f32("fd.blot_ws", int(w_off[-1]) * 4 if prepared else 4, dev)
         # ---- every table, one upload -------------------------------------------------
         T = _Tables()
         o_ib, o_db = T.add(ib, np.int32), T.add(db, np.int32)

@@ -46,6 +46,23 @@ def _workspace(nbytes, device):
     return ws
 
 
+_scratch_bufs = {}
+
+
+def scratch_f32(name, numel, device):
+    """Grow-only float32 scratch tensor per (name, device, stream): internal buffers of
+    the multi-kernel pipelines are reused across calls instead of going through the
+    allocator (reuse is ordered by the stream the kernels run on)."""
+    key = (name, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch_bufs.get(key)
+    if buf is None or buf.numel() < numel:
+        buf = None
+        _scratch_bufs.pop(key, None)
+        buf = torch.empty(max(int(numel), 1024), dtype=torch.float32, device=device)
+        _scratch_bufs[key] = buf
+    return buf
+
+
 def _f32c(t, name):
     if not t.is_cuda:
         raise ValueError(name + " must be a CUDA tensor")

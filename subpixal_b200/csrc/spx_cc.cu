@@ -9,6 +9,8 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "../../include/subpixal_b200.h"
 #include "spx_cc_engine.cuh"
 
@@ -388,7 +390,7 @@ static int launch(CcParams &prm, const SlabPlan &sp, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(cc_fit_kernel<C>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
-    const int grid = units_for(prm.n, sp) * C::CL;
+    int grid = units_for(prm.n, sp) * C::CL;
     if (C::CL == 1) {
         cc_fit_kernel<C><<<grid, C::T, smem, stream>>>(prm);
     } else {
@@ -399,6 +401,26 @@ static int launch(CcParams &prm, const SlabPlan &sp, cudaStream_t stream) {
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = C::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
+        // persistent grid: never more clusters than can be co-resident (GPCs with an odd
+        // number of usable SMs cannot pair all of them), or the tail runs as a second wave
+        static int max_clusters[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64) {
+            if (max_clusters[dev] == 0) {
+                int mc = 0;
+                cudaLaunchConfig_t q = cfg;
+                q.gridDim = dim3(num_sms() * C::MINB);
+                if (cudaOccupancyMaxActiveClusters(&mc, cc_fit_kernel<C>, &q) != cudaSuccess || mc <= 0) {
+                    cudaGetLastError();
+                    mc = -1;
+                }
+                max_clusters[dev] = mc;
+                if (getenv("SPX_DEBUG")) fprintf(stderr, "subpixal_b200: max active clusters = %d\n", mc);
+            }
+            if (max_clusters[dev] > 0 && grid > max_clusters[dev] * C::CL) grid = max_clusters[dev] * C::CL;
+        }
+        cfg.gridDim = dim3(grid);
         e = cudaLaunchKernelEx(&cfg, cc_fit_kernel<C>, prm);
         if (e != cudaSuccess) return int(e);
     }

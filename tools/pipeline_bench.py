@@ -26,11 +26,11 @@ def main():
         maps = blot.fit_pixel_maps(fmap, boxes, dbox)
         t_maps = (time.perf_counter() - t0) * 1e3
         fmap = None
-        for _ in range(2):
+        for _ in range(3):
             r = align.frame_displacements(img, drz, boxes, dbox, fmap, maps=maps)
         torch.cuda.synchronize()
         import time
-        reps = 5
+        reps = 20
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -71,7 +71,10 @@ using Cfg128 = CcCfg<192, 12, 16, 128, SPX128_T, 1, true,  true,  SPX128_INPLACE
 #else
 using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
 #endif
-using Cfg256 = CcCfg<384, 24, 16, 256, 256, 1, false, false>;
+#ifndef SPX256_T
+#define SPX256_T 512
+#endif
+using Cfg256 = CcCfg<384, 24, 16, 256, SPX256_T, 1, false, false>;
 
 template <class C> struct Layout {
     // shared memory carve-up (bytes); everything 16-byte aligned

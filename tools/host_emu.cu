@@ -113,7 +113,7 @@ int main(int argc, char **argv) {
     if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, true, true, EMU128_INPLACE, 2>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
-    else run<CcCfg<384, 24, 16, 256, 256, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else run<CcCfg<384, 24, 16, 256, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     f = fopen(argv[2], "wb");
     fwrite(shifts.data(), 8, shifts.size(), f);
     fwrite(peak.data(), 4, n, f);

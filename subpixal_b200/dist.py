@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "pack_results", "allgather_results", "cc_fit_frames_sharded",
-           "cc_fit_stack_sharded"]
+           "cc_fit_stack_sharded", "frame_displacements_sharded"]
 
 
 def shard_range(n, rank, world):
@@ -73,3 +73,22 @@ def cc_fit_stack_sharded(local_stack, n_total, cc_type="NCC", group=None):
     _, _, per = shard_range(n_total, rank, world)
     sh, pk, st, _ = batch.cc_fit_stack(local_stack, cc_type)
     return allgather_results(pack_results(sh, pk, st, per), n_total, group)
+
+
+def frame_displacements_sharded(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, group=None,
+                                maps=None, flux_scale=1.0, src_ids=None, **kw):
+    """``align.frame_displacements`` (gather + gather + blot + CC, all on the device)
+    with the source table sharded by rank; both frames are replicated.  Returns the
+    full ``(shifts, peak, status)`` table on every rank after ONE all-gather."""
+    import numpy as np
+    from . import align
+    rank, world = _rank_world(group)
+    ib = np.asarray(img_boxes).reshape(-1, 4)
+    db = np.asarray(drz_boxes).reshape(-1, 4)
+    n = ib.shape[0]
+    lo, hi, per = shard_range(n, rank, world)
+    part = lambda v: None if v is None else np.asarray(v)[lo:hi]
+    fs = flux_scale if np.ndim(flux_scale) == 0 else np.asarray(flux_scale)[lo:hi]
+    sh, pk, st = align.frame_displacements(img_frame, drz_frame, ib[lo:hi], db[lo:hi], frame_map,
+                                           flux_scale=fs, src_ids=part(src_ids), maps=part(maps), **kw)
+    return allgather_results(pack_results(sh, pk, st, per), n, group)

@@ -55,6 +55,27 @@ struct CcParams {
 #ifndef SPX64_MINB
 #define SPX64_MINB 2
 #endif
+// Intermediate classes with a power-of-two transform (P >= 1.5 n): pure radix-2/4 codelets,
+// generic (runtime-geometry) path only.  They exist for ragged batches - the bounding-box
+// cutouts of create_cutouts (cutout.py:159-175) are mostly 15-50 px wide.
+#ifndef SPX20_T
+#define SPX20_T 64
+#endif
+#ifndef SPX20_MINB
+#define SPX20_MINB 12
+#endif
+#ifndef SPX42_T
+#define SPX42_T 128
+#endif
+#ifndef SPX42_MINB
+#define SPX42_MINB 4
+#endif
+#ifndef SPX84_T
+#define SPX84_T 512
+#endif
+using Cfg20  = CcCfg< 32,  4,  8,  20, SPX20_T, SPX20_MINB, true,  true,  true>;
+using Cfg42  = CcCfg< 64,  8,  8,  42, SPX42_T, SPX42_MINB, true,  true,  true>;
+using Cfg84  = CcCfg<128,  8, 16,  84, SPX84_T, 1, true,  true,  true>;
 using Cfg32  = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32_MINB, true,  true,  true>;
 using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, true,  true,  true>;
 #ifndef SPX128_CLUSTER
@@ -365,8 +386,11 @@ static int num_sms() {
 
 static int pick_cfg(int ny, int nx) {
     const int m = ny > nx ? ny : nx;
+    if (m <= 20) return 20;
     if (m <= 32) return 32;
+    if (m <= 42) return 42;
     if (m <= 64) return 64;
+    if (m <= 84) return 84;
     if (m <= 128) return 128;
     if (m <= 256) return 256;
     return 0;
@@ -374,6 +398,9 @@ static int pick_cfg(int ny, int nx) {
 
 static SlabPlan plan_for(int cfg, int ny, int nx, bool want_icc) {
     switch (cfg) {
+        case 20: return plan_slab<Cfg20>(ny, nx, want_icc);
+        case 42: return plan_slab<Cfg42>(ny, nx, want_icc);
+        case 84: return plan_slab<Cfg84>(ny, nx, want_icc);
         case 32: return plan_slab<Cfg32>(ny, nx, want_icc);
         case 64: return plan_slab<Cfg64>(ny, nx, want_icc);
         case 128: return plan_slab<Cfg128>(ny, nx, want_icc);
@@ -447,6 +474,9 @@ static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *
     prm.off_icc = sp.off_icc; prm.off_w = sp.off_w; prm.off_r = sp.off_r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (cfg) {
+        case 20: return launch<Cfg20>(prm, sp, st);
+        case 42: return launch<Cfg42>(prm, sp, st);
+        case 84: return launch<Cfg84>(prm, sp, st);
         case 32: return launch<Cfg32>(prm, sp, st);
         case 64: return launch<Cfg64>(prm, sp, st);
         case 128: return launch<Cfg128>(prm, sp, st);

@@ -73,6 +73,9 @@ struct CcCfg {
     static constexpr int P = P_, E1 = E1_, E2 = E2_, NMAX = NMAX_, T = T_, MINB = MINB_;
     static constexpr bool W_SMEM = WSM_, R_SMEM = RSM_, INPLACE = INPLACE_;
     static constexpr int CL = CL_;
+    // the compile-time fast path for full-size interior cutouts places the tiles at
+    // offset NMAX/2, which must be a multiple of E2 (see c1_pass)
+    static constexpr bool HAS_FAST = (NMAX_ / 2) % E2_ == 0;
     static constexpr int NW = T / 32;
     static constexpr int NXL = NMAX / CL;    // tile columns loaded / finished by one CTA
     static constexpr int E1L = E1 / CL;      // k1 groups (of E2 rows each) held by one CTA
@@ -950,9 +953,13 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     const int nonfinite = SPX_S_NONFINITE_REF | SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
                           SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
     const bool check = job.cc_type == SPX_CC || (ps->status & (nonfinite | kSawNonFinite)) != 0;
-    if (fast) {
-        if (check) run_transforms<C, true, true>(c, ex);
-        else run_transforms<C, true, false>(c, ex);
+    if constexpr (C::HAS_FAST) {
+        if (fast) {
+            if (check) run_transforms<C, true, true>(c, ex);
+            else run_transforms<C, true, false>(c, ex);
+        } else {
+            run_transforms<C, false, true>(c, ex);
+        }
     } else {
         run_transforms<C, false, true>(c, ex);
     }

@@ -66,7 +66,22 @@ template <> __device__ __forceinline__ bool is_finite<double>(double v) {
 constexpr int kRowsPerWarp = SPX_GATHER_RPW;
 constexpr int kGatherRowsPerCta = kRowsPerWarp * (kGatherThreads / 32);
 
-template <class T, bool AUX>
+// DQB / SEGB: byte width of the dq / segmentation elements known at compile time
+// (0 = plane absent, -1 = decide at run time).  The common combinations (uint16 dq,
+// int32 / int64 segmentation) get their own instantiations so that the auxiliary
+// loads are plain, batched loads instead of a per-pixel switch on the width.
+template <int B> __device__ __forceinline__ long long load_bits_c(const void *p, long long i, int bytes) {
+    if constexpr (B == 2) return static_cast<const uint16_t *>(p)[i];
+    else if constexpr (B == 4) return static_cast<const uint32_t *>(p)[i];
+    else return load_bits(p, i, bytes);
+}
+template <int B> __device__ __forceinline__ long long load_int_c(const void *p, long long i, int bytes) {
+    if constexpr (B == 4) return static_cast<const int32_t *>(p)[i];
+    else if constexpr (B == 8) return static_cast<const long long *>(p)[i];
+    else return load_int(p, i, bytes);
+}
+
+template <class T, bool AUX, int DQB = -1, int SEGB = -1>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev a) {
     const int k = blockIdx.y;
     const int4 box = __ldg(reinterpret_cast<const int4 *>(a.boxes) + k);
@@ -79,19 +94,33 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev 
     const T *frame = static_cast<const T *>(a.frame);
     T *out = static_cast<T *>(a.data_out);
     const T fill = T(a.fillval);
-    const bool want_dq = AUX && a.dq != nullptr, want_seg = AUX && a.seg && a.src_ids;
+    const bool want_dq = AUX && DQB != 0 && a.dq != nullptr;
+    const bool want_seg = AUX && SEGB != 0 && a.seg && a.src_ids;
     const bool want_w = AUX && a.weight && a.weight_out;
     const int rbase = row0 + warp * kRowsPerWarp;
     for (int col = lane; col < w; col += 32) {
         const int xx = x1 + col;
         const bool incol = xx >= 0 && xx < a.W;
         T v[kRowsPerWarp];
+        long long dqv[kRowsPerWarp], sgv[kRowsPerWarp];
         bool inside[kRowsPerWarp];
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) {                       // pixel loads first
             const int row = rbase + r, yy = y1 + row;
             inside[r] = incol && row < h && yy >= 0 && yy < a.H;      // cutout.py:742-752
             v[r] = inside[r] ? __ldg(frame + (long long)yy * a.frame_pitch + xx) : fill;
+        }
+        if (AUX) {                                                     // then the auxiliary planes, batched
+#pragma unroll
+            for (int r = 0; r < kRowsPerWarp; ++r) {
+                const long long src = (long long)(y1 + rbase + r) * a.W + xx;
+                dqv[r] = (want_dq && inside[r]) ? load_bits_c<DQB>(a.dq, src, a.dq_bytes) : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < kRowsPerWarp; ++r) {
+                const long long src = (long long)(y1 + rbase + r) * a.W + xx;
+                sgv[r] = (want_seg && inside[r]) ? load_int_c<SEGB>(a.seg, src, a.seg_bytes) : 0;
+            }
         }
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) {
@@ -103,14 +132,10 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(const GatherDev 
             if (AUX) {
                 const long long src = (long long)(y1 + row) * a.W + xx;
                 if (want_dq) {                                         // cutout.py:758-766
-                    const long long d = inside[r] ? load_bits(a.dq, src, a.dq_bytes) : 0;
-                    if (a.dq_out) store_int(a.dq_out, o, a.dq_bytes, d);
-                    if (a.dq_use_bits) bad |= (d & ~a.dq_good_bits) != 0;   // cutout.py:190-193
+                    if (a.dq_out) store_int(a.dq_out, o, a.dq_bytes, dqv[r]);
+                    if (a.dq_use_bits) bad |= (dqv[r] & ~a.dq_good_bits) != 0;   // cutout.py:190-193
                 }
-                if (want_seg) {                                        // cutout.py:188, 416-419
-                    const long long sg = inside[r] ? load_int(a.seg, src, a.seg_bytes) : 0;
-                    bad |= (sg != sid);
-                }
+                if (want_seg) bad |= (sgv[r] != sid);                  // cutout.py:188, 416-419
                 if (want_w) {                                          // cutout.py:769-779
                     if (a.weight_f64)
                         static_cast<double *>(a.weight_out)[o] =
@@ -169,8 +194,16 @@ extern "C" int spx_gather_cutouts(const spx_gather_args *g, void *stream) {
         if (a.src_ids) b.src_ids = a.src_ids + k0;
         dim3 grid(rows, nk);
         if (g->frame_kind == SPX_T_F32) {
-            if (aux) gather_kernel<float, true><<<grid, kGatherThreads, 0, st>>>(b);
-            else gather_kernel<float, false><<<grid, kGatherThreads, 0, st>>>(b);
+            const bool has_seg = g->seg && g->src_ids;
+            const int dqb = g->dq ? a.dq_bytes : 0, sgb = has_seg ? a.seg_bytes : 0;
+            if (!aux) gather_kernel<float, false><<<grid, kGatherThreads, 0, st>>>(b);
+            else if (dqb == 2 && sgb == 4) gather_kernel<float, true, 2, 4><<<grid, kGatherThreads, 0, st>>>(b);
+            else if (dqb == 2 && sgb == 8) gather_kernel<float, true, 2, 8><<<grid, kGatherThreads, 0, st>>>(b);
+            else if (dqb == 2 && sgb == 0) gather_kernel<float, true, 2, 0><<<grid, kGatherThreads, 0, st>>>(b);
+            else if (dqb == 0 && sgb == 4) gather_kernel<float, true, 0, 4><<<grid, kGatherThreads, 0, st>>>(b);
+            else if (dqb == 0 && sgb == 8) gather_kernel<float, true, 0, 8><<<grid, kGatherThreads, 0, st>>>(b);
+            else if (dqb == 4 && sgb == 4) gather_kernel<float, true, 4, 4><<<grid, kGatherThreads, 0, st>>>(b);
+            else gather_kernel<float, true><<<grid, kGatherThreads, 0, st>>>(b);
         } else {
             if (aux) gather_kernel<double, true><<<grid, kGatherThreads, 0, st>>>(b);
             else gather_kernel<double, false><<<grid, kGatherThreads, 0, st>>>(b);

@@ -31,6 +31,19 @@
 #include "spx_fft.cuh"
 #include "spx_peak.cuh"
 
+// item loops of the passes: optional unrolling so that the loads of the next item
+// overlap the arithmetic of the current one (knobs for tools/variant.sh)
+#if defined(SPX_UNROLL_E2) && !defined(SPX_HOST_EMU)
+#define SPX_UNROLL_SMALL _Pragma("unroll 2")
+#else
+#define SPX_UNROLL_SMALL
+#endif
+#if defined(SPX_UNROLL_E1) && !defined(SPX_HOST_EMU)
+#define SPX_UNROLL_BIG _Pragma("unroll 2")
+#else
+#define SPX_UNROLL_BIG
+#endif
+
 namespace spx {
 
 // --------------------------------------------------------------------------
@@ -39,15 +52,17 @@ namespace spx {
 // two-step twiddle W_P^(n2*k1) from the [n2][k1] table (one of the two indices is
 // a compile-time constant at every call site -> base register + immediate)
 #ifndef SPX_HOST_EMU
-template <int P, int E1> __constant__ TwTable2<P, E1> c_tw2 = TwTable2<P, E1>();
+template <int P, int E1, bool INV> __constant__ TwTable2<P, E1, INV> c_tw2 = TwTable2<P, E1, INV>();
 #endif
-template <int P, int E1> struct HostTw2 { static const TwTable2<P, E1> t; };
-template <int P, int E1> const TwTable2<P, E1> HostTw2<P, E1>::t = TwTable2<P, E1>();
-template <class C> SPX_HD cf tw2(int n2, int k1) {
+template <int P, int E1, bool INV> struct HostTw2 { static const TwTable2<P, E1, INV> t; };
+template <int P, int E1, bool INV>
+const TwTable2<P, E1, INV> HostTw2<P, E1, INV>::t = TwTable2<P, E1, INV>();
+// forward twiddle W_P^(n2*k1) / its conjugate (inverse transforms)
+template <class C, bool INV = false> SPX_HD cf tw2(int n2, int k1) {
 #if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
-    return c_tw2<C::P, C::E1>.w[n2 * C::E1 + k1];
+    return c_tw2<C::P, C::E1, INV>.w[n2 * C::E1 + k1];
 #else
-    return HostTw2<C::P, C::E1>::t.w[n2 * C::E1 + k1];
+    return HostTw2<C::P, C::E1, INV>::t.w[n2 * C::E1 + k1];
 #endif
 }
 
@@ -354,6 +369,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
     constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
     static_assert(!FAST || (C::NMAX / 2) % C::E2 == 0, "fast path needs E2 | NMAX/2");
     int flags = 0;
+    SPX_UNROLL_BIG
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
         const bool active = FAST || i < nx;
@@ -436,6 +452,7 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
+    SPX_UNROLL_SMALL
     for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
         const int j = wi % C::E1L, i = (wi / C::E1L) * 32 + lane;
         if (i >= nx) continue;
@@ -458,6 +475,7 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
+    SPX_UNROLL_SMALL
     for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
         const int j = wi % C::E1L, l = (wi / C::E1L) * 32 + lane;
         const int k1 = j * C::CL + c.rank;
@@ -470,7 +488,7 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            c.W[(j * C::E2 + n2) * C::WP + l + col0] = cmulc(x[n2], tw2<C>(n2, k1));
+            c.W[(j * C::E2 + n2) * C::WP + l + col0] = cmul(x[n2], tw2<C, true>(n2, k1));
         });
     }
 }
@@ -489,6 +507,7 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
     float *icc = c.icc;
     const int cbase = 2 * c.col_lo;              // my columns start at surface column 2*col_lo
     Best best = best_init();
+    SPX_UNROLL_BIG
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
         const int n2 = wi % C::E2, l = (wi / C::E2) * 32 + lane;
         if (l >= nx) continue;
@@ -576,6 +595,7 @@ SPX_HD void x1_pass(const Ctx<C> &c, int tid, int cb, int ce, int xoff) {
     const int nx = FAST ? C::NMAX : c.ps->nx;
     constexpr int N1_LO = (FAST && !IS_REF) ? C::NMAX / (2 * C::E2) : 0;
     constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
+    SPX_UNROLL_BIG
     for (int wi = cb * C::E2 + warp; wi < ce * C::E2; wi += C::NW) {
         const int chunk = wi / C::E2, n2 = wi - chunk * C::E2;
         const int r = row_of<C, IS_REF>(c, chunk, lane);
@@ -612,6 +632,7 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int cb, int ce) {
     const int warp = warp_of(tid), lane = tid & 31;
     // normalisation scale and the 1/P^2 of the unnormalised inverse FFTs
     const float sc = c.ps->rscale * (1.0f / (float(C::P) * float(C::P)));
+    SPX_UNROLL_SMALL
     for (int wi = cb * C::E1 + warp; wi < ce * C::E1; wi += C::NW) {
         const int chunk = wi / C::E1, k1 = wi - chunk * C::E1;
         const int r = row_of<C, true>(c, chunk, lane);
@@ -637,6 +658,7 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int cb, int ce) {
 template <class C>
 SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
     const int warp = warp_of(tid), lane = tid & 31;
+    SPX_UNROLL_SMALL
     for (int wi = cb * C::E1 + warp; wi < ce * C::E1; wi += C::NW) {
         const int chunk = wi / C::E1, k1 = wi - chunk * C::E1;
         const int r = row_of<C, false>(c, chunk, lane);
@@ -666,7 +688,7 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            srow[k1 * C::E2 + n2] = cmulc(x[n2], tw2<C>(n2, k1));
+            srow[k1 * C::E2 + n2] = cmul(x[n2], tw2<C, true>(n2, k1));
         });
     }
 }
@@ -677,6 +699,7 @@ template <class C>
 SPX_HD void x3_pass(const Ctx<C> &c, int tid, int cb, int ce, int shift) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
+    SPX_UNROLL_BIG
     for (int wi = cb * C::E2 + warp; wi < ce * C::E2; wi += C::NW) {
         const int chunk = wi / C::E2, n2 = wi - chunk * C::E2;
         const int r = row_of<C, false>(c, chunk, lane);

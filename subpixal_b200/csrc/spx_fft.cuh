@@ -26,11 +26,13 @@ SPX_HD cf twmul(cf a) {
         constexpr float cr = (o == 1 || o == 7) ? 1.f : -1.f;
         constexpr float sfw = (o == 1 || o == 3) ? -1.f : 1.f;   // forward sin sign
         constexpr float ci = INV ? -sfw : sfw;
-        return cmake((cr * a.x - ci * a.y) * h, (ci * a.x + cr * a.y) * h);
+        // (cr + i ci) * a * h = (cr * a + ci * (i a)) * h  -  one packed add (the +-i
+        // and the signs are operand modifiers) and one packed multiply
+        return cscale(cadd(cmake(cr * a.x, cr * a.y), cmake(-ci * a.y, ci * a.x)), h);
     } else {
         constexpr float wr = float(cos2pi(k, N));
         constexpr float wi = float(INV ? sin2pi(k, N) : -sin2pi(k, N));
-        return cmake(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+        return cmul(a, cmake(wr, wi));
     }
 }
 
@@ -41,12 +43,13 @@ template <bool INV> SPX_HD void bfly2(cf &a, cf &b) {
 template <bool INV> SPX_HD void bfly3(cf &a, cf &b, cf &c) {
     constexpr float s = INV ? 0.86602540378443864676f : -0.86602540378443864676f;
     cf t1 = cadd(b, c);
-    cf t2 = cmake(a.x - 0.5f * t1.x, a.y - 0.5f * t1.y);
-    cf t3 = cmake(s * (b.x - c.x), s * (b.y - c.y));   // s*(b-c)
+    cf t2 = caxpy(t1, -0.5f, a);                        // a - t1/2
+    cf t3 = cscale(csub(b, c), s);                      // s*(b-c)
     a = cadd(a, t1);
     // X1 = t2 + i*t3 , X2 = t2 - i*t3     (i*(u+iv) = -v + iu)
-    b = cmake(t2.x - t3.y, t2.y + t3.x);
-    c = cmake(t2.x + t3.y, t2.y - t3.x);
+    cf it3 = cmake(-t3.y, t3.x);
+    b = cadd(t2, it3);
+    c = csub(t2, it3);
 }
 template <bool INV> SPX_HD void bfly4(cf &a, cf &b, cf &c, cf &d) {
     cf t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);

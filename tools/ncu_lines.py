@@ -72,7 +72,7 @@ agg = collections.defaultdict(lambda: [0, 0]); byop = collections.Counter(); tot
 byfn = collections.defaultdict(lambda: [0, 0])
 PASSES = ('c1_pass','c2_pass','x1_pass','x2_pass','x3_pass','ic1_pass','ic2_pass','x2_ref_pass','stats_thread','stats_finalize','peak_stage','process_pair')
 bypass = collections.defaultdict(lambda: collections.Counter())
-MATH = ('FADD','FMUL','FFMA'); MEM = ('LDS','STS','LDG','STG','LDC','LD','ST')
+MATH = ('FADD','FMUL','FFMA','FADD2','FMUL2','FFMA2'); MEM = ('LDS','STS','LDG','STG','LDC','LD','ST')
 for (loc, txt, chain), r in zip(seq, data):
     ins = int(r[ci['Instructions Executed']] or 0); s = int(r[ci['# Samples']] or 0)
     agg[loc][0] += ins; agg[loc][1] += s; tot += ins; ts += s

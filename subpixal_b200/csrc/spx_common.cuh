@@ -136,13 +136,6 @@ SPX_HD cf cmul(cf a, cf b) {
     return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 #endif
 }
-SPX_HD cf cmulc(cf a, cf b) {  // a * conj(b)
-#ifdef SPX_F32X2
-    return pk_fma(cmake(a.x, a.x), cmake(b.x, -b.y), pk_mul(cmake(a.y, a.y), cmake(b.y, b.x)));
-#else
-    return cmake(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-#endif
-}
 // a * (s, s) and a + b * (s, s) with a real scalar s
 SPX_HD cf cscale(cf a, float s) {
 #ifdef SPX_F32X2

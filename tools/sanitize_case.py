@@ -25,5 +25,32 @@ batch.find_peak_batch(torch.randn((5, 33, 47), device="cuda", generator=g))
 batch.find_peak_batch(torch.randn((5, 33, 47), device="cuda", generator=g, dtype=torch.float64),
                       guess=torch.tensor([[3.0, 4.0]] * 5), search_box=(5, 7), fit_box=(3, 5))
 batch.segment_boxes(torch.randint(0, 9, (70, 90), device="cuda", dtype=torch.int32, generator=g))
+# new size classes, ragged batches, blot (direct / prepared / linear / nearest), device pipeline
+for (ny, nx, n) in ((20, 20, 5), (13, 19, 3), (42, 42, 4), (33, 40, 3), (84, 84, 2), (70, 66, 2)):
+    st = torch.randn((n, 5, ny, nx), device="cuda", generator=g)
+    batch.cc_fit_stack(st, "NCC", want_icc=True)
+shapes = [(3, 5), (20, 37), (64, 64), (100, 90), (21, 19), (85, 60), (130, 140)]
+flat = torch.randn(sum(5 * a * b for a, b in shapes), device="cuda", generator=g)
+offs = np.concatenate([[0], np.cumsum([5 * a * b for a, b in shapes])])[:-1]
+batch.cc_fit_ragged(flat, offs, shapes, "ZNCC", want_icc=True)
+batch.cc_fit_ragged(flat, offs, shapes, "NCC")
+from subpixal_b200 import align, blot
+rng = np.random.default_rng(0)
+srcs = [(5, 4), (6, 6), (40, 33), (64, 80), (3, 70)]
+sflat = torch.randn(sum(a * b for a, b in srcs), device="cuda", generator=g)
+soff = np.concatenate([[0], np.cumsum([a * b for a, b in srcs])])[:-1]
+tg = [(7, 9), (6, 6), (32, 32), (64, 64), (16, 50)]
+def mk(k):
+    h, w = srcs[k]; ny, nx = tg[k]
+    return blot.fit_pixel_map(lambda x, y: (1 + (x - 1) * (w + 3.0) / nx - 1.5, 1 + (y - 1) * (h + 3.0) / ny - 1.5), nx, ny)
+maps = np.stack([mk(k) for k in range(len(srcs))])
+for interp, prep in (("poly5", True), ("poly5", False), ("linear", False), ("nearest", False)):
+    batch.blot_phases(sflat, soff, srcs, maps, tg, interp=interp, prepare=prep)
+ib = np.array([[-5, -5, 26, 20], [380, 270, 420, 310], [10, 10, 73, 73], [100, 100, 119, 119]])
+db = ib + np.array([-6, -6, 6, 6])
+seg = torch.randint(0, 3, (300, 400), device="cuda", dtype=torch.int32, generator=g)
+align.frame_displacements(frames[0], frames[1], ib, db, lambda x, y: (x + 0.3, y - 0.2),
+                          drz_seg=seg, src_ids=[1, 1, 2, 0], full_output=True)
+align.frame_displacements(frames[0], frames[1], ib, db, lambda x, y: (x + 0.3, y - 0.2))
 torch.cuda.synchronize()
 print("sanitize case done", float(out[0].sum()))

@@ -244,6 +244,7 @@ int spx_segment_boxes(const void *seg, int seg_kind, int h, int w, int64_t pitch
 #define SPX_BLOT_NEAREST 0
 #define SPX_BLOT_LINEAR  1
 #define SPX_BLOT_POLY5   2
+#define SPX_BLOT_POLY3   3   /* 4x4 cubic (drizzle's 'poly3') */
 
 typedef struct spx_blot_args {
     const float *src; const int64_t *src_offset; const int32_t *src_shape;

@@ -125,6 +125,34 @@ def interp_poly5(data, x, y):
     return _everett(*z, sy)
 
 
+def _everett3(fm1, f0, f1, f2, s):
+    """Cubic through four equally spaced samples (positions -1..2) at 0 <= s < 1
+    (IRAF ii_bipoly3: Everett's formula truncated after the second differences)."""
+    one, two = F(1), F(2)
+    s2 = s * s
+    t = one - s
+    t2 = t * t
+    cd20 = F(1.0 / 6.0) * ((f1 - two * f0) + fm1)
+    cd21 = F(1.0 / 6.0) * ((f2 - two * f1) + f0)
+    return s * (f1 + (s2 - one) * cd21) + t * (f0 + (t2 - one) * cd20)
+
+
+def interp_poly3(data, x, y):
+    """4x4 cubic interpolation of float32 ``data`` at 0-based float32 (x, y)."""
+    data = np.asarray(data, F)
+    x = np.asarray(x, F)
+    y = np.asarray(y, F)
+    ix = x.astype(np.int64)
+    iy = y.astype(np.int64)
+    sx = x - ix.astype(F)
+    sy = y - iy.astype(F)
+    z = []
+    for dj in range(-1, 3):
+        f = [_extended(data, iy + dj, ix + di) for di in range(-1, 3)]
+        z.append(_everett3(*f, sx))
+    return _everett3(*z, sy)
+
+
 def interp_linear(data, x, y):
     data = np.asarray(data, F)
     h, w = data.shape
@@ -150,7 +178,8 @@ def interp_nearest(data, x, y):
     return data[np.minimum(iy, h - 1), np.minimum(ix, w - 1)]
 
 
-INTERP = {"nearest": interp_nearest, "linear": interp_linear, "poly5": interp_poly5}
+INTERP = {"nearest": interp_nearest, "linear": interp_linear, "poly3": interp_poly3,
+          "poly5": interp_poly5}
 
 
 def blot_phases(src, coef, ny, nx, phases=((0.0, 0.0),), scale=1.0, misval=0.0,

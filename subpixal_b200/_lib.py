@@ -25,7 +25,7 @@ EXPORTS = ("spx_abi_version", "spx_error_string", "spx_gather_cutouts",
            "spx_cc_fit_frames",
            "spx_find_peak", "spx_segment_boxes", "spx_blot_phases",
            "spx_blot_workspace_bytes")
-BLOT_NEAREST, BLOT_LINEAR, BLOT_POLY5 = 0, 1, 2
+BLOT_NEAREST, BLOT_LINEAR, BLOT_POLY5, BLOT_POLY3 = 0, 1, 2, 3
 BLOT_MAX_PHASES = 8
 
 

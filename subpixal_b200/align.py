@@ -269,7 +269,7 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
         raise ValueError("The number of image cutouts must match the number "
                          "of drizzled cutouts.")
     if interp not in batch._BLOT_INTERP:
-        raise ValueError("interp %r is not supported on the GPU (nearest, linear, poly5)" % (interp,))
+        raise ValueError("interp %r is not supported on the GPU (nearest, linear, poly3, poly5)" % (interp,))
     for name, fr in (("img_frame", img_frame), ("drz_frame", drz_frame)):
         if not (fr.is_cuda and fr.dim() == 2 and fr.dtype == torch.float32 and fr.stride(1) == 1):
             raise ValueError(name + " must be a 2-D float32 CUDA tensor with unit column stride")

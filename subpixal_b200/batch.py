@@ -282,7 +282,8 @@ def gather_cutouts(frame, boxes, dq=None, weight=None, seg=None, src_ids=None,
     return out
 
 
-_BLOT_INTERP = {"nearest": L.BLOT_NEAREST, "linear": L.BLOT_LINEAR, "poly5": L.BLOT_POLY5}
+_BLOT_INTERP = {"nearest": L.BLOT_NEAREST, "linear": L.BLOT_LINEAR, "poly3": L.BLOT_POLY3,
+                "poly5": L.BLOT_POLY5}
 
 # align.py:664-679: blot to the image cutout, then with dx -= 0.5, dy -= 0.5 (both),
 # dy -= 0.5 alone.  Cutout.dx -= 0.5 moves the cutout grid by +0.5 px in the image
@@ -311,7 +312,7 @@ def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00
     require_cuda()
     lib = L.load()
     if interp not in _BLOT_INTERP:
-        raise ValueError("interp %r is not supported on the GPU (nearest, linear, poly5)"
+        raise ValueError("interp %r is not supported on the GPU (nearest, linear, poly3, poly5)"
                          % (interp,))
     src = _f32c(src, "src").reshape(-1)
     dev = src.device

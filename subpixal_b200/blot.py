@@ -15,7 +15,7 @@ Differences from the reference, by construction:
   cutout (corners, edge mid-points, centre) and the interpolating biquadratic is
   evaluated on the device (float64).  Over a cutout of <= 256 px the cubic terms
   of HST distortion models are < 1e-4 px.
-* only ``interp`` in {'nearest', 'linear', 'poly5'} is implemented on the GPU
+* only ``interp`` in {'nearest', 'linear', 'poly3', 'poly5'} is implemented on the GPU
   ('poly5' is the reference's default and the only one align.py uses); the other
   drizzle kernels raise ``NotImplementedError``.
 * drizzlepac is an un-vendored dependency that is absent here: the interpolator
@@ -32,8 +32,8 @@ from . import batch
 __all__ = ['BlotWCSMap', 'blot_cutout', 'blot_phases', 'fit_pixel_map', 'fit_pixel_maps',
            'pixel_ratio']
 
-_SUPPORTED = ('nearest', 'linear', 'poly5')
-_DRIZZLE_ONLY = ('poly3', 'spline3', 'sinc', 'lanczos3', 'lanczos5')
+_SUPPORTED = ('nearest', 'linear', 'poly3', 'poly5')
+_DRIZZLE_ONLY = ('spline3', 'sinc', 'lanczos3', 'lanczos5')
 
 
 class BlotWCSMap(object):

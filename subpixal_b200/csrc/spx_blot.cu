@@ -99,6 +99,39 @@ __device__ __forceinline__ float poly5(const float *d, int h, int w, float x, fl
     return everett(z[0], z[1], z[2], z[3], z[4], z[5], sy);
 }
 
+// cubic through four equally spaced samples (positions -1..2) at 0 <= s < 1
+__device__ __forceinline__ float everett3(float fm1, float f0, float f1, float f2, float s) {
+    const float s2 = fm(s, s), t = fs(1.f, s), t2 = fm(t, t);
+    const float cd20 = fm(1.0f / 6.0f, fa(fs(f1, fm(2.f, f0)), fm1));
+    const float cd21 = fm(1.0f / 6.0f, fa(fs(f2, fm(2.f, f1)), f0));
+    return fa(fm(s, fa(f1, fm(fs(s2, 1.f), cd21))), fm(t, fa(f0, fm(fs(t2, 1.f), cd20))));
+}
+
+__device__ __forceinline__ float poly3(const float *d, int h, int w, float x, float y) {
+    const int ix = int(x), iy = int(y);
+    const float sx = fs(x, float(ix)), sy = fs(y, float(iy));
+    float z[4];
+    if (ix >= 1 && ix + 2 < w && iy >= 1 && iy + 2 < h) {           // interior: plain loads
+        const float *p = d + (long long)(iy - 1) * w + (ix - 1);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float f[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) f[c] = __ldg(p + (long long)r * w + c);
+            z[r] = everett3(f[0], f[1], f[2], f[3], sx);
+        }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            float f[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) f[c] = ext_sample(d, h, w, iy - 1 + r, ix - 1 + c);
+            z[r] = everett3(f[0], f[1], f[2], f[3], sx);
+        }
+    }
+    return everett3(z[0], z[1], z[2], z[3], sy);
+}
+
 // ---- prepared sources ------------------------------------------------------------
 // The x-direction central differences of Everett's formula belong to the SOURCE
 // sample, not to the output pixel: cd2(c) = (E(c+1) - 2E(c) + E(c-1))/6 and
@@ -236,6 +269,7 @@ __global__ void __launch_bounds__(kBlotThreads) blot_kernel(const BlotDev a) {
         if (x >= 0.f && x <= xmax && y >= 0.f && y <= ymax) {
             float t;
             if (INTERP == SPX_BLOT_POLY5) t = PREP ? poly5_prepared(ws, w, x, y) : poly5(d, h, w, x, y);
+            else if (INTERP == SPX_BLOT_POLY3) t = poly3(d, h, w, x, y);
             else if (INTERP == SPX_BLOT_LINEAR) t = bilinear(d, h, w, x, y);
             else t = nearest(d, h, w, x, y);
             val = fm(t, scale);
@@ -261,7 +295,8 @@ extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
     if (!g.src || !g.src_offset || !g.src_shape || !g.map || !g.tgt_shape || !g.out_offset ||
         !g.out || g.max_ny < 1 || g.max_nx < 1)
         return SPX_E_BADARG;
-    if (g.interp != SPX_BLOT_NEAREST && g.interp != SPX_BLOT_LINEAR && g.interp != SPX_BLOT_POLY5)
+    if (g.interp != SPX_BLOT_NEAREST && g.interp != SPX_BLOT_LINEAR && g.interp != SPX_BLOT_POLY5 &&
+        g.interp != SPX_BLOT_POLY3)
         return SPX_E_UNSUPPORTED;
     if (g.n > 65535 * 64) return SPX_E_UNSUPPORTED;
     BlotDev a;
@@ -296,6 +331,7 @@ extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
             blot_prep_kernel<<<dim3(px, cnt), kBlotThreads, 0, st>>>(b);
             blot_kernel<SPX_BLOT_POLY5, true><<<grid, kBlotThreads, 0, st>>>(b);
         } else if (g.interp == SPX_BLOT_POLY5) blot_kernel<SPX_BLOT_POLY5, false><<<grid, kBlotThreads, 0, st>>>(b);
+        else if (g.interp == SPX_BLOT_POLY3) blot_kernel<SPX_BLOT_POLY3, false><<<grid, kBlotThreads, 0, st>>>(b);
         else if (g.interp == SPX_BLOT_LINEAR) blot_kernel<SPX_BLOT_LINEAR, false><<<grid, kBlotThreads, 0, st>>>(b);
         else blot_kernel<SPX_BLOT_NEAREST, false><<<grid, kBlotThreads, 0, st>>>(b);
     }

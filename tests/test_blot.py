@@ -45,7 +45,12 @@ def test_oracle_edge_extension_is_exact_for_planes_and_hits_the_samples():
     assert np.max(np.abs(got - (2 + 0.5 * x.astype(np.float64) - 0.25 * y))) < 1e-5
     data = rng.standard_normal((h, w)).astype(np.float32)
     jj, ii = np.mgrid[0:h, 0:w]
-    for fn in (bo.interp_poly5, bo.interp_linear, bo.interp_nearest):
+    cubic = (1 + 0.3 * xx - 0.2 * yy + 0.01 * xx * yy + 1e-3 * xx ** 2 - 2e-4 * yy ** 3).astype(np.float32)
+    xi = rng.uniform(1, w - 3, 500).astype(np.float32); yi = rng.uniform(1, h - 3, 500).astype(np.float32)
+    want = (1 + 0.3 * xi.astype(np.float64) - 0.2 * yi + 0.01 * xi.astype(np.float64) * yi
+            + 1e-3 * xi.astype(np.float64) ** 2 - 2e-4 * yi.astype(np.float64) ** 3)
+    assert np.max(np.abs(bo.interp_poly3(cubic, xi, yi) - want)) < 2e-5     # cubics are reproduced
+    for fn in (bo.interp_poly5, bo.interp_poly3, bo.interp_linear, bo.interp_nearest):
         got = fn(data, ii.ravel().astype(np.float32), jj.ravel().astype(np.float32))
         assert np.allclose(got.reshape(h, w), data, atol=2e-6)
     # a 6x6 stencil on an image smaller than the stencil still works (folded + clamped)
@@ -157,8 +162,8 @@ def _random_case(rng, k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("interp,prepare", [("poly5", True), ("poly5", False), ("linear", False),
-                                            ("nearest", False)])
+@pytest.mark.parametrize("interp,prepare", [("poly5", True), ("poly5", False), ("poly3", False),
+                                            ("linear", False), ("nearest", False)])
 def test_gpu_blot_is_bit_identical_to_the_oracle(interp, prepare):
     from subpixal_b200 import batch
     rng = np.random.default_rng(7)

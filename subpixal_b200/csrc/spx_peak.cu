@@ -8,7 +8,7 @@
 
 namespace spx {
 
-constexpr int kPeakThreads = 256;
+constexpr int kPeakThreads = 128;
 
 struct PeakParams {
     const void *surf; const unsigned char *mask; const double *guess;
@@ -28,7 +28,7 @@ __device__ __forceinline__ double py2round_dev(double x) {        // utils.py:14
 }
 
 template <class T>
-__global__ void __launch_bounds__(kPeakThreads, 4) find_peak_kernel(const PeakParams p) {
+__global__ void __launch_bounds__(kPeakThreads, 8) find_peak_kernel(const PeakParams p) {
     __shared__ double s_v[kPeakThreads / 32];
     __shared__ int s_i[kPeakThreads / 32];
     const int k = blockIdx.x;
@@ -60,22 +60,49 @@ __global__ void __launch_bounds__(kPeakThreads, 4) find_peak_kernel(const PeakPa
         const int bw = sx2 - sx1, cnt = bw * (sy2 - sy1);
         if (bw == p.w && sizeof(T) == 4 && !use_mask && (cnt & 3) == 0 &&
             (reinterpret_cast<size_t>(img + sy1 * p.w) & 15) == 0) {
-            // contiguous float32 samples, 16-byte aligned: 128-bit loads, two in flight
+            // contiguous float32 samples, 16-byte aligned: four 128-bit loads in flight per
+            // thread.  float -> double is exact and monotonic, so the comparison runs in
+            // float32 (the reference upcasts first, centroid.py:98): one NaN-propagating
+            // max over the 16 samples decides whether the index search is needed at all.
             const int base = sy1 * p.w;
             const float4 *v4 = reinterpret_cast<const float4 *>(img + base);
             const int n4 = cnt >> 2;
-            for (int t0 = tid; t0 < n4; t0 += 2 * kPeakThreads) {
-                const int t1 = t0 + kPeakThreads;
-                const float4 a = __ldg(v4 + t0);
-                const float4 b = t1 < n4 ? __ldg(v4 + t1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float va[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float bv = -INFINITY;           // running first maximum of this thread (NaN wins)
+            int bi = 0x7fffffff;
+            for (int t0 = tid; t0 < n4; t0 += 4 * kPeakThreads) {
+                float4 q[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (u >= 4 && t1 >= n4) break;
-                    BestD c; c.v = double(va[u]); c.idx = base + 4 * (u < 4 ? t0 : t1) + (u & 3);
-                    if (!found || bestd_better(c, best)) { best = c; found = true; }
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + u * kPeakThreads;
+                    q[u] = t < n4 ? __ldg(v4 + t) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                }
+                float m = -INFINITY;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float m4;
+                    asm("max.NaN.f32 %0, %1, %2;" : "=f"(m4) : "f"(q[u].x), "f"(q[u].y));
+                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(m4) : "f"(q[u].z));
+                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(m4) : "f"(q[u].w));
+                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(m4));
+                }
+                // padding (-inf) never wins: bi stays unset until a real sample is seen
+                if ((bv == bv) && (!(m <= bv) || bi == 0x7fffffff)) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u * kPeakThreads;
+                        if (t >= n4) break;
+                        const float va[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float v = va[e];
+                            if ((bv == bv) && (v != v || v > bv || bi == 0x7fffffff)) {
+                                bv = v; bi = base + 4 * t + e;
+                            }
+                        }
+                    }
                 }
             }
+            if (bi != 0x7fffffff) { best.v = double(bv); best.idx = bi; found = true; }
         } else if (bw == p.w) {
             // full-width window: the samples are contiguous, no div/mod, four
             // independent loads in flight per thread

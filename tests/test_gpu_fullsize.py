@@ -138,3 +138,60 @@ def test_100k_boxes_128_properties():
     sub = torch.arange(0, 100000, 97, device="cuda")
     sh3, pk3, _, _ = batch.cc_fit_frames(frames, boxes[sub], 128, 128, "NCC")
     assert torch.equal(sh3, sh[sub]) and torch.equal(pk3, pk[sub])
+
+
+def test_pipeline_10k_sources_and_ragged_100k():
+    """Device-only per-image pipeline at config-2 size (10 000 sources: gather x2 +
+    blot x4 phases + ragged CC) and a 100 000-pair ragged batch, through properties."""
+    from subpixal_b200 import align, batch, blot, synthetic as syn
+    sc = syn.make_scene(10000, 2048, 4096, 64, seed=20242)
+    frames, truth = syn.make_frames(sc, "cuda")
+    img, ref00 = frames[0], frames[1]              # the image and the undisplaced reference frame
+    boxes = syn.make_boxes(sc).astype(np.int64)
+    dbox = boxes + np.array([-8, -8, 8, 8])
+    ident = lambda x, y: (x, y)
+    maps = blot.fit_pixel_maps(ident, boxes, dbox)
+    sh, pk, st = align.frame_displacements(img, ref00, boxes, dbox, None, maps=maps)
+    sh_h = sh.cpu().numpy()
+    assert np.all(np.isfinite(sh_h)) and int((st != 0).sum()) < 50
+    # blotting the phase-00 reference frame through the identity map at the four half-pixel
+    # phases reproduces (up to the quintic interpolation error) the four rendered phase
+    # frames, so the pipeline must agree with the frame-based path on the same scene
+    shf, _, _, _ = batch.cc_fit_frames(frames, torch.from_numpy(boxes.astype(np.int32)).cuda(), 64, 64, "NCC")
+    d = (sh - shf).abs().cpu().numpy()
+    assert np.median(d) < 5e-3 and np.percentile(d, 99) < 5e-2
+    err = sh_h - truth
+    assert abs(np.median(err[:, 0])) < 0.02 and abs(np.median(err[:, 1])) < 0.02
+    # determinism and permutation invariance of the whole pipeline
+    sh2, pk2, _ = align.frame_displacements(img, ref00, boxes, dbox, None, maps=maps)
+    assert torch.equal(sh, sh2) and torch.equal(pk, pk2)
+    perm = np.random.default_rng(3).permutation(10000)
+    sh3, _, _ = align.frame_displacements(img, ref00, boxes[perm], dbox[perm], None, maps=maps[perm])
+    assert torch.equal(sh3, sh[torch.from_numpy(perm).cuda()])
+    # the blot of the identity map at phase (0,0) is the source itself inside the frame
+    k = 17
+    ny = nx = 64
+    ph = batch.blot_phases(ref00.contiguous().reshape(-1), [0], [ref00.shape],
+                           blot.fit_pixel_maps(ident, boxes[k:k + 1], [[0, 0, 4095, 2047]]), [(ny, nx)])[0]
+    want = ref00[boxes[k, 1]:boxes[k, 1] + ny, boxes[k, 0]:boxes[k, 0] + nx]
+    assert float((ph[:ny * nx].view(ny, nx) - want).abs().max()) <= 2e-6 * float(want.abs().max())
+
+    # ---- 100 000 ragged pairs: every pair equals its own uniform launch (sampled), the
+    # table is independent of the order in which the size classes are visited
+    rng = np.random.default_rng(11)
+    sizes = rng.integers(6, 70, (100000, 2))
+    tiles = sizes[:, 0] * sizes[:, 1]
+    offs = np.concatenate([[0], np.cumsum(5 * tiles)])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    flat = torch.randn(int(offs[-1]), device="cuda", generator=g)
+    r = batch.cc_fit_ragged(flat, offs[:-1], sizes, "NCC")
+    sh_r, pk_r = r[0].cpu().numpy(), r[1].cpu().numpy()
+    assert np.all(np.isfinite(sh_r))
+    for k in rng.integers(0, 100000, 40):
+        nyk, nxk = int(sizes[k, 0]), int(sizes[k, 1])
+        st5 = flat[offs[k]:offs[k + 1]].view(1, 5, nyk, nxk)
+        u = batch.cc_fit_stack(st5.contiguous(), "NCC")
+        assert np.array_equal(u[0].cpu().numpy()[0], sh_r[k]) and int(u[1][0]) == pk_r[k]
+    rev = np.arange(100000)[::-1].copy()
+    r2 = batch.cc_fit_ragged(flat, offs[:-1][rev], sizes[rev], "NCC")
+    assert np.array_equal(r2[0].cpu().numpy(), sh_r[rev]) and np.array_equal(r2[1].cpu().numpy(), pk_r[rev])

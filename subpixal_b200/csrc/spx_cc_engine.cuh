@@ -369,8 +369,8 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
     constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
     static_assert(!FAST || (C::NMAX / 2) % C::E2 == 0, "fast path needs E2 | NMAX/2");
     int flags = 0;
-    SPX_UNROLL_BIG
-    for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
+    // an item = (32-column chunk, n2): its loads, and everything after them
+    auto load_item = [&](int wi, float (&va)[C::E1], float (&vb)[C::E1]) {
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
         const bool active = FAST || i < nx;
         const TileCol ta = tile_col(ps, sa, c.col_lo + i, active);
@@ -379,8 +379,6 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
         const int rs = C::E2 * ta.pitch;                     // elements between loads
         const float *pa0 = ta.p + ybase * ta.pitch;
         const float *pb0 = tb.p + ybase * tb.pitch;
-        // all loads first (independent), arithmetic afterwards
-        float va[C::E1], vb[C::E1];
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             if constexpr (FAST) {
@@ -397,6 +395,11 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
                 vb[n1] = (ok && tb.colok) ? ld_f32_last(pb0 + n1 * rs) : 0.f;
             }
         });
+    };
+    auto finish_item = [&](int wi, float (&va)[C::E1], float (&vb)[C::E1]) {
+        const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
+        const bool active = FAST || i < nx;
+        const int ybase = n2 - yoff;
         // one cheap test for "any NaN/Inf among my pixels": max of |bits|
         unsigned worst = 0u;
         if constexpr (CHECK) {
@@ -441,6 +444,33 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
                 cf *wb = w_of_k1<C, k1>(c.W, c.Wpeer, c.rank);   // owner of the k1 group
                 wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gi] = cmul(x[k1], tw2<C>(n2, k1));
             });
+        }
+    };
+    const int nitems = nchunk * C::E2;
+    // 16 loads per item on the fast path: two items fit the 64 px class's registers
+    // (+1.6 %; the 32 and 128 px classes spill and lose 2-4 %)
+#if !defined(SPX_HOST_EMU) && !defined(SPX_NO_C1_PAIR)
+    constexpr bool kPairItems = FAST && C::NMAX == 64;
+#else
+    constexpr bool kPairItems = false;
+#endif
+    if constexpr (kPairItems) {
+        // two items per iteration: the tile loads of the second (L2 latency) are in flight
+        // while the first goes through its FFT
+        for (int wi = warp; wi < nitems; wi += 2 * C::NW) {
+            float va0[C::E1], vb0[C::E1], va1[C::E1], vb1[C::E1];
+            const bool two = wi + C::NW < nitems;            // warp-uniform
+            load_item(wi, va0, vb0);
+            if (two) load_item(wi + C::NW, va1, vb1);
+            finish_item(wi, va0, vb0);
+            if (two) finish_item(wi + C::NW, va1, vb1);
+        }
+    } else {
+        SPX_UNROLL_BIG
+        for (int wi = warp; wi < nitems; wi += C::NW) {
+            float va[C::E1], vb[C::E1];
+            load_item(wi, va, vb);                           // all loads first (independent)
+            finish_item(wi, va, vb);                         // arithmetic afterwards
         }
     }
     return flags;

@@ -266,7 +266,10 @@ SPX_HD StatPartial stats_thread(const Ctx<C> &c, int tid) {
     // Pixels outside [ylo,yhi) x [xlo,xhi) are fill pixels: zero in every tile, so
     // they take part in no sum (cc.py:134-137 masks zeros).  The five tiles share
     // the box geometry, so one element offset serves all five base pointers.
-    constexpr int U = 4;                                     // rows in flight per lane
+#ifndef SPX_STATS_U
+#define SPX_STATS_U 4
+#endif
+    constexpr int U = SPX_STATS_U;                           // rows in flight per lane
     for (int x = xlo + lane; x < xhi; x += 32) {
         const long long off = (long long)(ps.y0[0] + ylo + warp) * pitch + (x + ps.x0[0]);
         const float *p[5];

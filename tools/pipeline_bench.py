@@ -31,14 +31,16 @@ def main():
         torch.cuda.synchronize()
         import time
         reps = 20
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            r = align.frame_displacements(img, drz, boxes, dbox, fmap, maps=maps)
-        e1.record(); torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) / reps * 1e3
-        ms = e0.elapsed_time(e1) / reps
+        best = (1e9, 1e9)
+        for _ in range(3):                       # best of three timing blocks (first-use effects)
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                r = align.frame_displacements(img, drz, boxes, dbox, fmap, maps=maps)
+            e1.record(); torch.cuda.synchronize()
+            best = min(best, (e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) / reps * 1e3))
+        ms, wall = best
         out.append({"pipeline": "gather x2 + blot x4 phases + ragged CC+fit", "n": n, "cutout": n_side,
                     "ms_device_span": ms, "ms_wall_incl_host_tables": wall, "ms_host_map_fit_9_points_per_source": t_maps, "pairs_per_s": n / (ms / 1e3),
                     "median_shift": np.median(r[0].cpu().numpy(), axis=0).tolist()})

@@ -309,3 +309,36 @@ def test_frame_pipeline_matches_the_cutout_object_path():
     g = icc.cpu().numpy()[ioff[k]:ioff[k + 1]].reshape(2 * ny, 2 * nx)
     assert np.linalg.norm(g - iccs[k]) / np.linalg.norm(iccs[k]) < 1e-5
     assert int((st.cpu().numpy() != 0).sum()) == 0
+
+
+def test_oracle_matches_its_frozen_outputs():
+    """tests/golden/blot_oracle.npz (made by tests/golden/make_blot_golden.py) freezes the
+    restatement - it is NOT a reference output, drizzlepac being unavailable."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "blot_oracle.npz"))
+    for k in range(4):
+        ny, nx = (int(v) for v in g["shape%d" % k])
+        for interp in ("poly5", "poly3", "linear", "nearest"):
+            got = bo.blot_phases(g["src%d" % k], g["map%d" % k], ny, nx, phases=PHASES, scale=0.75,
+                                 misval=-2.0, interp=interp)
+            assert np.array_equal(got.view(np.uint32), g["%s%d" % (interp, k)].view(np.uint32)), (k, interp)
+
+
+@pytest.mark.gpu
+def test_gpu_blot_matches_the_frozen_oracle_outputs():
+    import os
+    from subpixal_b200 import batch
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "blot_oracle.npz"))
+    srcs = [g["src%d" % k] for k in range(4)]
+    shp = np.array([s.shape for s in srcs])
+    off = np.concatenate([[0], np.cumsum(shp[:, 0] * shp[:, 1])])[:-1]
+    tg = np.array([g["shape%d" % k] for k in range(4)])
+    maps = np.stack([g["map%d" % k] for k in range(4)])
+    flat = torch.from_numpy(np.concatenate([s.ravel() for s in srcs])).cuda()
+    for interp in ("poly5", "poly3", "linear", "nearest"):
+        out, o = batch.blot_phases(flat, off, shp, maps, tg, phases=PHASES, scale=np.full(4, 0.75, np.float32),
+                                   interp=interp, misval=-2.0)
+        out = out.cpu().numpy()
+        for k in range(4):
+            want = g["%s%d" % (interp, k)]
+            assert np.array_equal(out[o[k]:o[k + 1]].reshape(want.shape).view(np.uint32), want.view(np.uint32))

@@ -1,5 +1,7 @@
 """Developer tool: compare tools/host_emu (CPU emulation of the CUDA pass
-sequence) with the oracle.  Not used by the product or by the test-suite."""
+sequence) with the oracle.  Not used by the product; kept under tests/ because it
+imports the oracle.  Build the emulator first:
+    g++ -std=c++17 -DSPX_HOST_EMU -O2 -x c++ -o /tmp/host_emu tools/host_emu.cu -lpthread"""
 import os, struct, subprocess, sys, warnings
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

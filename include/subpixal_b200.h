@@ -148,7 +148,7 @@ int spx_cc_fit_stack(const float *ref, const float *im00, const float *im10,
  * order      [n] int32 device: the pairs this launch processes (outputs are
  *            written at index p = order[k], so several launches can fill one
  *            table), or NULL for 0..n-1.  Every processed pair must fit the
- *            size class of (max_ny, max_nx) - 20, 32, 42, 64, 84, 128 or 256 px; the
+ *            size class of (max_ny, max_nx) - 20, 32, 42, 64, 84, 128, 170 or 256 px; the
  *            caller buckets pairs by class (one launch per class) because a
  *            pair costs as much as the largest shape of its class.
  * icc        ragged output: surface p at element icc_offsets[p], or NULL.

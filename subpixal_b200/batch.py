@@ -108,7 +108,7 @@ def cc_fit_stack(stack, cc_type="NCC", want_icc=False):
     return shifts, peak, status, icc
 
 
-_SIZE_CLASSES = (20, 32, 42, 64, 84, 128, 256)     # pick_cfg() in csrc/spx_cc.cu
+_SIZE_CLASSES = (20, 32, 42, 64, 84, 128, 170, 256)     # pick_cfg() in csrc/spx_cc.cu
 
 
 def cc_fit_ragged(stack, offsets, shapes, cc_type="NCC", want_icc=False):
@@ -116,7 +116,7 @@ def cc_fit_ragged(stack, offsets, shapes, cc_type="NCC", want_icc=False):
     block ``[5, ny_p, nx_p]`` at element ``offsets[p]`` of the flat float32 CUDA
     tensor ``stack``, ``shapes[p] = (ny_p, nx_p)`` (ragged cutouts of
     create_cutouts, reference cutout.py:159-175; cc.py:21-95 per pair).  Pairs are
-    bucketed by size class (20/32/42/64/84/128/256 px) - one launch per class.  Returns
+    bucketed by size class (20/32/42/64/84/128/170/256 px) - one launch per class.  Returns
     ``(shifts [n,2] f64, peak [n] i32, status [n] i32, icc, icc_offsets)`` with
     ``icc`` a flat float32 tensor holding surface p (``[2ny_p, 2nx_p]``) at
     ``icc_offsets[p]`` (both None unless ``want_icc``)."""

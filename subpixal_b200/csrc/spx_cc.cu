@@ -76,6 +76,7 @@ struct CcParams {
 using Cfg20  = CcCfg< 32,  4,  8,  20, SPX20_T, SPX20_MINB, true,  true,  true>;
 using Cfg42  = CcCfg< 64,  8,  8,  42, SPX42_T, SPX42_MINB, true,  true,  true>;
 using Cfg84  = CcCfg<128,  8, 16,  84, SPX84_T, 1, true,  true,  true>;
+using Cfg170 = CcCfg<256, 16, 16, 170, 512, 1, false, false>;              // W / R in a global slab
 using Cfg32  = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32_MINB, true,  true,  true>;
 using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, true,  true,  true>;
 #ifndef SPX128_CLUSTER
@@ -392,6 +393,7 @@ static int pick_cfg(int ny, int nx) {
     if (m <= 64) return 64;
     if (m <= 84) return 84;
     if (m <= 128) return 128;
+    if (m <= 170) return 170;
     if (m <= 256) return 256;
     return 0;
 }
@@ -401,6 +403,7 @@ static SlabPlan plan_for(int cfg, int ny, int nx, bool want_icc) {
         case 20: return plan_slab<Cfg20>(ny, nx, want_icc);
         case 42: return plan_slab<Cfg42>(ny, nx, want_icc);
         case 84: return plan_slab<Cfg84>(ny, nx, want_icc);
+        case 170: return plan_slab<Cfg170>(ny, nx, want_icc);
         case 32: return plan_slab<Cfg32>(ny, nx, want_icc);
         case 64: return plan_slab<Cfg64>(ny, nx, want_icc);
         case 128: return plan_slab<Cfg128>(ny, nx, want_icc);
@@ -477,6 +480,7 @@ static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *
         case 20: return launch<Cfg20>(prm, sp, st);
         case 42: return launch<Cfg42>(prm, sp, st);
         case 84: return launch<Cfg84>(prm, sp, st);
+        case 170: return launch<Cfg170>(prm, sp, st);
         case 32: return launch<Cfg32>(prm, sp, st);
         case 64: return launch<Cfg64>(prm, sp, st);
         case 128: return launch<Cfg128>(prm, sp, st);

@@ -339,7 +339,7 @@ def test_ragged_stack_matches_uniform_launches_and_oracle():
     import subpixal_b200._lib as L
     shapes = [(3, 5), (20, 37), (32, 32), (33, 40), (64, 64), (64, 64), (17, 64), (100, 90),
               (128, 128), (130, 200), (256, 256), (6, 6), (48, 48), (64, 64), (20, 20), (21, 19),
-              (42, 42), (84, 84), (70, 66), (85, 60)]
+              (42, 42), (84, 84), (70, 66), (85, 60), (170, 170), (150, 129)]
     pairs = [orc.random_pairs(1, ny, nx, seed=900 + k, masked=(k % 3 == 0))[0][0]
              for k, (ny, nx) in enumerate(shapes)]
     sizes = np.array([5 * ny * nx for ny, nx in shapes])

@@ -16,7 +16,7 @@ def main():
     out = []
     gen = torch.Generator(device="cuda").manual_seed(1)
     cases = ((32, 100000), (64, 25000), (128, 6000), (256, 1500), (48, 40000), (100, 8000),
-             (20, 200000), (42, 50000), (84, 12000))
+             (20, 200000), (42, 50000), (84, 12000), (170, 3000))
     if len(sys.argv) > 1:
         want = [int(v) for v in sys.argv[1].split(",")]
         cases = tuple(c for c in cases if c[0] in want)

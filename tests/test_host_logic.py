@@ -155,3 +155,31 @@ def test_shard_range_covers_everything():
                 got += list(range(lo, hi))
             assert got == list(range(n))
             assert per * world >= n
+
+
+def test_pipeline_table_packing_is_aligned_and_ordered():
+    """align._Tables: every per-source table of frame_displacements lands 16-byte aligned
+    in ONE staging buffer, in insertion order (the device pointers are base + offset)."""
+    from subpixal_b200.align import _Tables
+    t = _Tables()
+    a = t.add(np.arange(7), np.int32)             # 28 bytes -> next table starts at 32
+    b = t.add(np.arange(3), np.float64)
+    c = t.add(np.zeros((5, 20)), np.float64)
+    d = t.add(np.arange(2), np.int64)
+    assert (a, b, c) == (0, 32, 64) and d == 64 + 800 and t.size == d + 16
+    assert all(off % 16 == 0 for off, _ in t.parts)
+    assert [arr.dtype for _, arr in t.parts] == [np.int32, np.float64, np.float64, np.int64]
+
+
+def test_size_classes_of_the_python_side_match_the_library():
+    """batch._SIZE_CLASSES lists the class boundaries of pick_cfg() in csrc/spx_cc.cu; the
+    boundaries of the classes that keep W / R in a global slab show in the workspace size."""
+    import subpixal_b200._lib as L
+    from subpixal_b200 import batch
+    lib = L.load()
+    ws = lambda n: lib.spx_cc_workspace_bytes(1, n, n, 0)
+    assert batch._SIZE_CLASSES[-1] == L.MAX_CUTOUT and 128 in batch._SIZE_CLASSES and 170 in batch._SIZE_CLASSES
+    assert ws(129) > ws(128) + 500000          # 129 px: first class with a W / R slab (P = 256)
+    assert ws(171) > ws(170) + 500000          # 171 px: P = 384
+    assert ws(170) - ws(129) < 300000          # inside a class only the surface scratch grows
+    assert lib.spx_cc_workspace_bytes(1, L.MAX_CUTOUT + 1, 8, 0) == 0

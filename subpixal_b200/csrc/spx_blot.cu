@@ -22,6 +22,9 @@ namespace spx {
 
 constexpr int kBlotThreads = 256;
 constexpr int kMaxPhases = 8;
+#ifndef SPX_BLOT_SMEM_TABLE_MAX
+#define SPX_BLOT_SMEM_TABLE_MAX (44 * 1024)      // >= 5 CTAs per SM (sources up to about 50 px); larger tables are faster through L2
+#endif
 
 struct BlotDev {
     const float *src; const long long *src_off; const int *src_shape;
@@ -146,6 +149,26 @@ __host__ __device__ __forceinline__ long long prep_elems(int h, int w) {
     return (long long)(h + kPadRows) * (w + 1);
 }
 
+// entry t of the prepared table of one source (padded row t / (w+1), column t % (w+1))
+__device__ __forceinline__ float4 prep_entry(const float *d, int h, int w, int r, int c) {
+    const int j = r - 2;
+    float e[5];
+    if (j >= 0 && j < h && c >= 2 && c + 2 < w) {                 // interior: plain loads
+        const float *p = d + (long long)j * w + (c - 2);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) e[k] = __ldg(p + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) e[k] = ext_sample(d, h, w, j, c - 2 + k);
+    }
+    float4 o;
+    o.x = e[2];
+    o.y = fm(1.0f / 6.0f, fa(fs(e[3], fm(2.f, e[2])), e[1]));
+    o.z = fm(1.0f / 120.0f, fa(fs(fa(fs(e[0], fm(4.f, e[1])), fm(6.f, e[2])), fm(4.f, e[3])), e[4]));
+    o.w = 0.f;
+    return o;
+}
+
 __global__ void __launch_bounds__(kBlotThreads) blot_prep_kernel(const BlotDev a) {
     const int s = blockIdx.y;
     const int h = a.src_shape[2 * s], w = a.src_shape[2 * s + 1];
@@ -155,22 +178,7 @@ __global__ void __launch_bounds__(kBlotThreads) blot_prep_kernel(const BlotDev a
     const int pw = w + 1, total = (h + kPadRows) * pw;
     for (int t = blockIdx.x * kBlotThreads + threadIdx.x; t < total; t += gridDim.x * kBlotThreads) {
         const int r = t / pw, c = t - r * pw;
-        const int j = r - 2;
-        float e[5];
-        if (j >= 0 && j < h && c >= 2 && c + 2 < w) {                 // interior: plain loads
-            const float *p = d + (long long)j * w + (c - 2);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) e[k] = __ldg(p + k);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) e[k] = ext_sample(d, h, w, j, c - 2 + k);
-        }
-        float4 o;
-        o.x = e[2];
-        o.y = fm(1.0f / 6.0f, fa(fs(e[3], fm(2.f, e[2])), e[1]));
-        o.z = fm(1.0f / 120.0f, fa(fs(fa(fs(e[0], fm(4.f, e[1])), fm(6.f, e[2])), fm(4.f, e[3])), e[4]));
-        o.w = 0.f;
-        ws[t] = o;
+        ws[t] = prep_entry(d, h, w, r, c);
     }
 }
 
@@ -182,6 +190,7 @@ __device__ __forceinline__ float everett_row(float4 p0, float4 p1, float s, floa
     return fa(a, b);
 }
 
+template <bool SMEM>
 __device__ __forceinline__ float poly5_prepared(const float4 *ws, int w, float x, float y) {
     const int ix = int(x), iy = int(y);
     const float sx = fs(x, float(ix)), sy = fs(y, float(iy));
@@ -191,8 +200,13 @@ __device__ __forceinline__ float poly5_prepared(const float4 *ws, int w, float x
     float4 q[12];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-        q[2 * r] = __ldg(p + (long long)r * (w + 1));
-        q[2 * r + 1] = __ldg(p + (long long)r * (w + 1) + 1);
+        if (SMEM) {                      // table in shared memory: plain (LDS.128) loads
+            q[2 * r] = p[r * (w + 1)];
+            q[2 * r + 1] = p[r * (w + 1) + 1];
+        } else {
+            q[2 * r] = __ldg(p + (long long)r * (w + 1));
+            q[2 * r + 1] = __ldg(p + (long long)r * (w + 1) + 1);
+        }
     }
     float z[6];
 #pragma unroll
@@ -221,18 +235,29 @@ __device__ __forceinline__ double dma(double a, double b, double c) {   // a*b +
     return __dadd_rn(__dmul_rn(a, b), c);
 }
 
-template <int INTERP, bool PREP>
+// PREP: 0 = direct evaluation, 1 = prepared table in global memory (blot_prep_kernel),
+// 2 = one CTA per source builds the table in its shared memory first (sources small enough:
+// no table traffic to and from L2 / HBM, no second launch)
+template <int INTERP, int PREP>
 __global__ void __launch_bounds__(kBlotThreads) blot_kernel(const BlotDev a) {
+    extern __shared__ float4 s_tab[];
     const int s = blockIdx.y;
     const int h = a.src_shape[2 * s], w = a.src_shape[2 * s + 1];
     const int ny = a.tgt_shape[2 * s], nx = a.tgt_shape[2 * s + 1];
     if (h < 1 || w < 1 || ny < 1 || nx < 1) return;
     const float *d = a.src + a.src_off[s];
     float *out = a.out + a.out_off[s];
-    const float4 *ws = PREP ? a.ws + a.ws_off[s] : nullptr;
+    const float4 *ws = PREP == 1 ? a.ws + a.ws_off[s] : (PREP == 2 ? s_tab : nullptr);
     // the map's 20 coefficients: shared memory, re-read at the start of every row
     __shared__ double cf[20];
     if (threadIdx.x < 20) cf[threadIdx.x] = __ldg(a.map + 20 * (long long)s + threadIdx.x);
+    if (PREP == 2) {
+        const int pw = w + 1, total = (h + kPadRows) * pw;
+        for (int t = threadIdx.x; t < total; t += kBlotThreads) {
+            const int r = t / pw, c = t - r * pw;
+            s_tab[t] = prep_entry(d, h, w, r, c);
+        }
+    }
     __syncthreads();
     const double xc = cf[0], yc = cf[1];
     const float scale = a.scale ? a.scale[s] : 1.f;
@@ -268,7 +293,9 @@ __global__ void __launch_bounds__(kBlotThreads) blot_kernel(const BlotDev a) {
         float val = a.misval;
         if (x >= 0.f && x <= xmax && y >= 0.f && y <= ymax) {
             float t;
-            if (INTERP == SPX_BLOT_POLY5) t = PREP ? poly5_prepared(ws, w, x, y) : poly5(d, h, w, x, y);
+            if (INTERP == SPX_BLOT_POLY5)
+                t = PREP == 2 ? poly5_prepared<true>(ws, w, x, y)
+                  : PREP == 1 ? poly5_prepared<false>(ws, w, x, y) : poly5(d, h, w, x, y);
             else if (INTERP == SPX_BLOT_POLY3) t = poly3(d, h, w, x, y);
             else if (INTERP == SPX_BLOT_LINEAR) t = bilinear(d, h, w, x, y);
             else t = nearest(d, h, w, x, y);
@@ -306,6 +333,15 @@ extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
     a.out = g.out; a.nph = g.nph; a.interp = g.interp; a.misval = g.misval;
     const bool prep = g.interp == SPX_BLOT_POLY5 && g.workspace != nullptr;
     if (prep && (!g.ws_offset || g.max_src_h < 1 || g.max_src_w < 1)) return SPX_E_BADARG;
+    // sources whose prepared table fits half an SM's shared memory: the table is built by
+    // the CTA that uses it (chosen when the caller asked for the prepared path at all)
+    const size_t smem_bytes = prep ? size_t(prep_elems(g.max_src_h, g.max_src_w)) * sizeof(float4) : 0;
+    const bool smem_tab = prep && smem_bytes <= SPX_BLOT_SMEM_TABLE_MAX;
+    if (smem_tab) {
+        cudaError_t ea = cudaFuncSetAttribute(blot_kernel<SPX_BLOT_POLY5, 2>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
+        if (ea != cudaSuccess) return int(ea);
+    }
     a.ws = static_cast<float4 *>(g.workspace);
     a.ws_off = reinterpret_cast<const long long *>(g.ws_offset);
     for (int k = 0; k < g.nph; ++k) { a.ph[k][0] = g.phases_host[2 * k]; a.ph[k][1] = g.phases_host[2 * k + 1]; }
@@ -324,16 +360,18 @@ extern "C" int spx_blot_phases(const spx_blot_args *args_host, void *stream) {
         b.tgt_shape += 2 * s0; b.out_off += s0;
         if (prep) b.ws_off += s0;
         const dim3 grid(bx, cnt);
-        if (prep) {
+        if (smem_tab) {
+            blot_kernel<SPX_BLOT_POLY5, 2><<<dim3(1, cnt), kBlotThreads, smem_bytes, st>>>(b);
+        } else if (prep) {
             const long long pe = prep_elems(g.max_src_h, g.max_src_w);
             int px = int((pe + 4 * kBlotThreads - 1) / (4 * kBlotThreads));
             px = px < 1 ? 1 : (px > 64 ? 64 : px);
             blot_prep_kernel<<<dim3(px, cnt), kBlotThreads, 0, st>>>(b);
-            blot_kernel<SPX_BLOT_POLY5, true><<<grid, kBlotThreads, 0, st>>>(b);
-        } else if (g.interp == SPX_BLOT_POLY5) blot_kernel<SPX_BLOT_POLY5, false><<<grid, kBlotThreads, 0, st>>>(b);
-        else if (g.interp == SPX_BLOT_POLY3) blot_kernel<SPX_BLOT_POLY3, false><<<grid, kBlotThreads, 0, st>>>(b);
-        else if (g.interp == SPX_BLOT_LINEAR) blot_kernel<SPX_BLOT_LINEAR, false><<<grid, kBlotThreads, 0, st>>>(b);
-        else blot_kernel<SPX_BLOT_NEAREST, false><<<grid, kBlotThreads, 0, st>>>(b);
+            blot_kernel<SPX_BLOT_POLY5, 1><<<grid, kBlotThreads, 0, st>>>(b);
+        } else if (g.interp == SPX_BLOT_POLY5) blot_kernel<SPX_BLOT_POLY5, 0><<<grid, kBlotThreads, 0, st>>>(b);
+        else if (g.interp == SPX_BLOT_POLY3) blot_kernel<SPX_BLOT_POLY3, 0><<<grid, kBlotThreads, 0, st>>>(b);
+        else if (g.interp == SPX_BLOT_LINEAR) blot_kernel<SPX_BLOT_LINEAR, 0><<<grid, kBlotThreads, 0, st>>>(b);
+        else blot_kernel<SPX_BLOT_NEAREST, 0><<<grid, kBlotThreads, 0, st>>>(b);
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : int(e);

@@ -238,7 +238,7 @@ class _Tables(object):
 
 def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, flux_scale=1.0,
                         cc_type="NCC", drz_seg=None, src_ids=None, interp="poly5",
-                        full_output=False, maps=None):
+                        full_output=False, maps=None, max_scratch_bytes=8 << 30):
     """The measurement half of ``_align_1image`` (align.py:464-560 -> 561-699) for one
     image, entirely on the device: crop the image cutouts (``img_boxes``) and the
     drizzled cutouts (``drz_boxes``; pixels of other segments zeroed when ``drz_seg``
@@ -256,7 +256,9 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
     Returns ``(shifts [n,2] f64, peak [n] i32, status [n] i32)`` CUDA tensors, plus
     ``(icc, icc_offsets)`` when ``full_output``.  The per-source tables travel in one
     asynchronous upload; the launches (2 gathers, blot preparation, blot, one CC+fit
-    per size class) are only enqueued - nothing here waits for the device."""
+    per size class) are only enqueued - nothing here waits for the device.  Source
+    tables whose cutout stacks would need more than ``max_scratch_bytes`` of device
+    scratch are processed in consecutive chunks."""
     import ctypes as C
     from . import _lib as L
     from . import blot as gpu_blot
@@ -283,6 +285,24 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
         raise L.SubpixalError("subpixal_b200: cutouts must be between %d and %d pixels per axis"
                               % (L.MIN_CUTOUT, L.MAX_CUTOUT))
     tiles = t_shp[:, 0] * t_shp[:, 1]
+    # scratch per source: ragged CC stack + blot source + prepared blot table
+    need = 20 * tiles + 4 * s_shp[:, 0] * s_shp[:, 1] + 16 * (s_shp[:, 0] + 5) * (s_shp[:, 1] + 1)
+    if n > 1 and int(need.sum()) > int(max_scratch_bytes):
+        cuts = np.flatnonzero(np.diff(np.cumsum(need) // int(max_scratch_bytes))) + 1
+        bounds = [0] + [int(c) for c in cuts] + [n]
+        sel = lambda v, a, b: v if v is None or np.ndim(v) == 0 else np.asarray(v)[a:b]
+        parts = [frame_displacements(img_frame, drz_frame, ib[a:b], db[a:b], frame_map,
+                                     flux_scale=sel(flux_scale, a, b), cc_type=cc_type, drz_seg=drz_seg,
+                                     src_ids=sel(src_ids, a, b), interp=interp, full_output=full_output,
+                                     maps=sel(maps, a, b), max_scratch_bytes=1 << 62)
+                 for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        out = [torch.cat([q[k] for q in parts]) for k in range(3)]
+        if full_output:
+            out.append(torch.cat([q[3] for q in parts]))
+            base = np.concatenate([[0], np.cumsum([int(q[4][-1]) for q in parts])])
+            out.append(np.concatenate([np.asarray(q[4][:-1]) + base[k] for k, q in enumerate(parts)] +
+                                      [[base[-1]]]))
+        return tuple(out)
     p_off = np.concatenate([[0], np.cumsum(5 * tiles)]).astype(np.int64)
     s_off = np.concatenate([[0], np.cumsum(s_shp[:, 0] * s_shp[:, 1])]).astype(np.int64)
     w_units = (s_shp[:, 0] + 5) * (s_shp[:, 1] + 1)               # spx_blot_workspace_bytes / 16

@@ -309,6 +309,12 @@ def test_frame_pipeline_matches_the_cutout_object_path():
     g = icc.cpu().numpy()[ioff[k]:ioff[k + 1]].reshape(2 * ny, 2 * nx)
     assert np.linalg.norm(g - iccs[k]) / np.linalg.norm(iccs[k]) < 1e-5
     assert int((st.cpu().numpy() != 0).sum()) == 0
+    # chunked processing (device scratch budget) gives the same table and the same surfaces
+    sh2, pk2, st2, icc2, ioff2 = align.frame_displacements(
+        torch.from_numpy(img).cuda(), torch.from_numpy(drz).cuda(), ib, db, frame_map,
+        flux_scale=1.0 / pr ** 2, full_output=True, max_scratch_bytes=150000)
+    assert torch.equal(sh, sh2) and torch.equal(pk, pk2) and torch.equal(st, st2)
+    assert torch.equal(icc, icc2) and np.array_equal(np.asarray(ioff), np.asarray(ioff2))
 
 
 def test_oracle_matches_its_frozen_outputs():

@@ -70,6 +70,8 @@ extern "C" {
 #define SPX_S_BOX_MISMATCH    0x400 /* fused path: box size != (ny, nx)       */
 #define SPX_S_FEW_POINTS      0x800 /* < 6 usable points (centroid.py:160,186,202) */
 #define SPX_S_SINGULAR       0x1000 /* rank-deficient masked fit (find_peak only) */
+#define SPX_S_UNSUPPORTED_SIZE 0x2000 /* ragged batch: an axis < 3 or > 256 px; shift NaN,
+                                        peak -1 (set by the host binding, the pair is not launched) */
 
 /* ---- element kinds for the gather --------------------------------------- */
 #define SPX_T_F32 0

@@ -18,6 +18,7 @@ S_NONFINITE_REF = 0x001
 S_NONFINITE_P00, S_NONFINITE_P10, S_NONFINITE_P01, S_NONFINITE_P11 = 0x2, 0x4, 0x8, 0x10
 S_BAD_NORM, S_PEAK_EDGE, S_NO_MAXIMUM, S_FIT_OUTSIDE = 0x20, 0x40, 0x80, 0x100
 S_FIT_NONFINITE, S_BOX_MISMATCH, S_FEW_POINTS, S_SINGULAR = 0x200, 0x400, 0x800, 0x1000
+S_UNSUPPORTED_SIZE = 0x2000
 T_F32, T_F64, T_I8, T_I16, T_I32, T_I64 = 0, 1, 2, 3, 4, 5
 
 EXPORTS = ("spx_abi_version", "spx_error_string", "spx_gather_cutouts",

@@ -238,13 +238,17 @@ class _Tables(object):
 
 def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, flux_scale=1.0,
                         cc_type="NCC", drz_seg=None, src_ids=None, interp="poly5",
-                        full_output=False, maps=None, max_scratch_bytes=8 << 30):
+                        full_output=False, maps=None, max_scratch_bytes=1 << 30,
+                        drz_dq=None, drz_dqbitmask=0):
     """The measurement half of ``_align_1image`` (align.py:464-560 -> 561-699) for one
     image, entirely on the device: crop the image cutouts (``img_boxes``) and the
     drizzled cutouts (``drz_boxes``; pixels of other segments zeroed when ``drz_seg``
     and ``src_ids`` are given, cutout.py:416-427 + align.py:661), blot every drizzled
     cutout onto its image cutout's grid at the four half-pixel phases
-    (align.py:664-679), cross-correlate and fit (cc.py:21-95).
+    (align.py:664-679), cross-correlate and fit (cc.py:21-95).  ``drz_dq`` (integer CUDA
+    tensor of the drizzled frame's shape) with ``drz_dqbitmask`` (the "good" bits, as
+    in create_cutouts; None ignores the DQ array) also zeroes drizzled pixels with bad
+    DQ bits - the ``create_cutouts(drz_dq=...)`` -> ``dzct.mask`` -> align.py:661 path.
 
     ``img_frame`` / ``drz_frame``: 2-D float32 CUDA tensors; boxes ``[n, 4]``
     (x1, y1, x2, y2), trc inclusive, sizes may differ between sources;
@@ -258,7 +262,9 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
     asynchronous upload; the launches (2 gathers, blot preparation, blot, one CC+fit
     per size class) are only enqueued - nothing here waits for the device.  Source
     tables whose cutout stacks would need more than ``max_scratch_bytes`` of device
-    scratch are processed in consecutive chunks."""
+    scratch are processed in consecutive chunks (``batch.clear_scratch()`` releases the
+    cached scratch).  Sources whose image cutout has an axis under 3 or over 256 px are
+    not processed: NaN shift, peak -1, status ``S_UNSUPPORTED_SIZE``."""
     import ctypes as C
     from . import _lib as L
     from . import blot as gpu_blot
@@ -281,9 +287,30 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
     if n and (t_shp.min() < 1 or s_shp.min() < 1):
         raise ValueError("Ill-formed extraction box")
     big = t_shp.max(axis=1) if n else np.zeros(0, np.int64)
-    if n and (t_shp.min() < L.MIN_CUTOUT or big.max() > L.MAX_CUTOUT):
-        raise L.SubpixalError("subpixal_b200: cutouts must be between %d and %d pixels per axis"
-                              % (L.MIN_CUTOUT, L.MAX_CUTOUT))
+    unsupported = (t_shp.min(axis=1) < L.MIN_CUTOUT) | (big > L.MAX_CUTOUT) if n \
+        else np.zeros(0, bool)
+    if unsupported.any():
+        # run the supported sources and scatter their results into NaN-filled tables
+        ok = np.flatnonzero(~unsupported)
+        sel = lambda v: v if v is None or np.ndim(v) == 0 else np.asarray(v)[ok]
+        sub = frame_displacements(img_frame, drz_frame, ib[ok], db[ok], frame_map,
+                                  flux_scale=sel(flux_scale), cc_type=cc_type, drz_seg=drz_seg,
+                                  src_ids=sel(src_ids), interp=interp, full_output=full_output,
+                                  maps=sel(maps), max_scratch_bytes=max_scratch_bytes,
+                                  drz_dq=drz_dq, drz_dqbitmask=drz_dqbitmask)
+        d_ok = torch.from_numpy(ok).to(dev)
+        shifts = torch.full((n, 2), float("nan"), dtype=torch.float64, device=dev)
+        peak = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        status = torch.full((n,), L.S_UNSUPPORTED_SIZE, dtype=torch.int32, device=dev)
+        shifts[d_ok], peak[d_ok], status[d_ok] = sub[0], sub[1], sub[2]
+        if not full_output:
+            return shifts, peak, status
+        sizes = 4 * t_shp[:, 0] * t_shp[:, 1]
+        i_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        icc = torch.full((int(i_off[-1]),), float("nan"), dtype=torch.float32, device=dev)
+        for j, k in enumerate(ok):
+            icc[int(i_off[k]):int(i_off[k + 1])] = sub[3][int(sub[4][j]):int(sub[4][j + 1])]
+        return shifts, peak, status, icc, i_off
     tiles = t_shp[:, 0] * t_shp[:, 1]
     # scratch per source: ragged CC stack + blot source + prepared blot table
     need = 20 * tiles + 4 * s_shp[:, 0] * s_shp[:, 1] + 16 * (s_shp[:, 0] + 5) * (s_shp[:, 1] + 1)
@@ -294,7 +321,8 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
         parts = [frame_displacements(img_frame, drz_frame, ib[a:b], db[a:b], frame_map,
                                      flux_scale=sel(flux_scale, a, b), cc_type=cc_type, drz_seg=drz_seg,
                                      src_ids=sel(src_ids, a, b), interp=interp, full_output=full_output,
-                                     maps=sel(maps, a, b), max_scratch_bytes=1 << 62)
+                                     maps=sel(maps, a, b), max_scratch_bytes=1 << 62,
+                                     drz_dq=drz_dq, drz_dqbitmask=drz_dqbitmask)
                  for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
         out = [torch.cat([q[k] for q in parts]) for k in range(3)]
         if full_output:
@@ -345,9 +373,12 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
         T.upload(dev)
         st = batch._stream()
         # ---- image cutouts -> slot 0 of the ragged stack; drizzled cutouts -> blot sources
-        for frame, o_box, o_off, out, hw, zero, seg in (
-                (img_frame, o_ib, o_poff, stack, t_shp, 0, None),
-                (drz_frame, o_db, o_soff, src, s_shp, 1, drz_seg if use_seg else None)):
+        from .cutout import interpret_bit_flags
+        good_bits = interpret_bit_flags(drz_dqbitmask) if drz_dq is not None else None
+        for frame, o_box, o_off, out, hw, zero, seg, dq in (
+                (img_frame, o_ib, o_poff, stack, t_shp, 0, None, None),
+                (drz_frame, o_db, o_soff, src, s_shp, 1, drz_seg if use_seg else None,
+                 drz_dq if good_bits is not None else None)):
             a = L.GatherArgs()
             a.frame, a.frame_kind = frame.data_ptr(), L.T_F32
             a.frame_h, a.frame_w, a.frame_pitch = int(frame.shape[0]), int(frame.shape[1]), int(frame.stride(0))
@@ -356,6 +387,13 @@ def frame_displacements(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, f
                     raise ValueError("segmentation image must be int32/int64 with the frame's shape")
                 seg = seg.contiguous()
                 a.seg, a.seg_kind, a.src_ids = seg.data_ptr(), batch._KIND[seg.dtype], T.ptr(o_ids)
+            if dq is not None:
+                if (tuple(dq.shape) != tuple(frame.shape) or dq.dtype not in batch._KIND
+                        or dq.is_floating_point() or not dq.is_cuda):
+                    raise ValueError("DQ image must be an integer CUDA tensor with the frame's shape")
+                dq = dq.contiguous()
+                a.dq, a.dq_kind = dq.data_ptr(), batch._KIND[dq.dtype]
+                a.dq_use_bits, a.dq_good_bits = 1, int(good_bits)
             a.boxes, a.out_offset, a.n = T.ptr(o_box), T.ptr(o_off), n
             a.max_h, a.max_w = int(hw[:, 0].max()), int(hw[:, 1].max())
             a.fillval, a.zero_masked = 0.0, zero
@@ -447,12 +485,24 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
     npts = len(img_cutouts)
     xyim = np.empty((npts, 2), dtype=np.float64)
     xyref = np.empty_like(xyim)
+    # sources the kernels could not process (an axis over 256 px: S_UNSUPPORTED_SIZE) come
+    # back with a NaN shift; they stay in the tables but get zero weight in the fit
+    unusable = ~np.isfinite(img_dxy).all(axis=1)
+    if unusable.any():
+        import warnings
+        warnings.warn("subpixal_b200: %d of %d sources have no displacement (cutout larger "
+                      "than 256 px or smaller than 3 px) and are left out of the fit"
+                      % (int(unusable.sum()), npts))
     for k, imct in enumerate(img_cutouts):                             # align.py:692-699
         x1, y1 = imct.cutout_src_pos
         xyim[k] = np.array(wcslin.wcs_world2pix(*imct.pix2world(x1, y1), 1)).ravel()
+        if unusable[k]:
+            xyref[k] = xyim[k]
+            continue
         xyref[k] = np.array(wcslin.wcs_world2pix(
             *imct.pix2world(x1 + img_dxy[k, 0], y1 + img_dxy[k, 1]), 1)).ravel()
     ref_dxy = xyim - xyref
+    ref_dxy[unusable] = np.nan
 
     weights = None
     if use_weights:                                                    # align.py:703-717
@@ -468,7 +518,11 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
         else:
             weights = np.asarray(weights, dtype=np.float64)
 
-    fit = iter_linear_fit(xyim, xyref, wxy=None, wuv=weights, fitgeom=fitgeom,
+    fit_weights = weights
+    if unusable.any():
+        fit_weights = np.ones(npts) if weights is None else weights.copy()
+        fit_weights[unusable] = 0.0
+    fit = iter_linear_fit(xyim, xyref, wxy=None, wuv=fit_weights, fitgeom=fitgeom,
                           center=np.array(wcslin.wcs.crpix), nclip=nclip, sigma=sigma)
     fit['subpixal_img_dxy'] = img_dxy
     fit['subpixal_ref_dxy'] = ref_dxy

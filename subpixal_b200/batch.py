@@ -40,27 +40,46 @@ def _ptr(t):
 def _workspace(nbytes, device):
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+    nbytes = max(int(nbytes), 1 << 20)
+    if ws is None or ws.numel() < nbytes or (ws.numel() > _SCRATCH_SLACK * nbytes and
+                                             ws.numel() > (64 << 20)):
+        ws = None
+        _workspaces.pop(key, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
 
 _scratch_bufs = {}
+_SCRATCH_SLACK = 4        # a cached buffer this many times larger than the request is dropped
 
 
 def scratch_f32(name, numel, device):
-    """Grow-only float32 scratch tensor per (name, device, stream): internal buffers of
-    the multi-kernel pipelines are reused across calls instead of going through the
-    allocator (reuse is ordered by the stream the kernels run on)."""
+    """float32 scratch tensor per (name, device, stream): internal buffers of the
+    multi-kernel pipelines are reused across calls instead of going through the
+    allocator (reuse is ordered by the stream the kernels run on).  A cached buffer
+    that is too small, or more than ``_SCRATCH_SLACK`` times larger than the request
+    (and above 64 MiB), is handed back to torch's caching allocator; ``clear_scratch()``
+    releases everything."""
     key = (name, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch_bufs.get(key)
-    if buf is None or buf.numel() < numel:
+    numel = max(int(numel), 1024)
+    if buf is not None and (buf.numel() < numel or
+                            (buf.numel() > _SCRATCH_SLACK * numel and buf.numel() > (16 << 20))):
         buf = None
         _scratch_bufs.pop(key, None)
-        buf = torch.empty(max(int(numel), 1024), dtype=torch.float32, device=device)
+    if buf is None:
+        buf = torch.empty(numel, dtype=torch.float32, device=device)
         _scratch_bufs[key] = buf
     return buf
+
+
+def clear_scratch():
+    """Release the cached scratch buffers and kernel workspaces of every device and
+    stream (they return to torch's caching allocator; ``torch.cuda.empty_cache()``
+    then gives the memory back to the driver)."""
+    _scratch_bufs.clear()
+    _workspaces.clear()
 
 
 def _f32c(t, name):
@@ -119,7 +138,10 @@ def cc_fit_ragged(stack, offsets, shapes, cc_type="NCC", want_icc=False):
     bucketed by size class (20/32/42/64/84/128/170/256 px) - one launch per class.  Returns
     ``(shifts [n,2] f64, peak [n] i32, status [n] i32, icc, icc_offsets)`` with
     ``icc`` a flat float32 tensor holding surface p (``[2ny_p, 2nx_p]``) at
-    ``icc_offsets[p]`` (both None unless ``want_icc``)."""
+    ``icc_offsets[p]`` (both None unless ``want_icc``).  A pair outside the supported
+    range (an axis under 3 or over 256 px - e.g. one extended source among the segment
+    boxes of create_cutouts) does not abort the batch: it gets a NaN shift, peak -1,
+    status ``S_UNSUPPORTED_SIZE`` and an all-NaN surface."""
     require_cuda()
     lib = L.load()
     stack = _f32c(stack, "stack").reshape(-1)
@@ -130,10 +152,12 @@ def cc_fit_ragged(stack, offsets, shapes, cc_type="NCC", want_icc=False):
     if off.numel() != n:
         raise ValueError("offsets and shapes must describe the same number of pairs")
     big = shp.max(dim=1).values if n else shp.new_zeros(0)
-    if n and (int(shp.min()) < L.MIN_CUTOUT or int(big.max()) > L.MAX_CUTOUT):
-        raise L.SubpixalError("subpixal_b200: cutouts must be between %d and %d pixels per axis"
-                              % (L.MIN_CUTOUT, L.MAX_CUTOUT))
-    if n and int((off + 5 * shp[:, 0].long() * shp[:, 1].long()).max()) > stack.numel():
+    if n and int(shp.min()) < 1:
+        raise ValueError("Cutouts must be 2D images.")
+    unsupported = ((shp.min(dim=1).values < L.MIN_CUTOUT) | (big > L.MAX_CUTOUT)) if n \
+        else torch.zeros(0, dtype=torch.bool)
+    if n and (int(off.min()) < 0 or
+              int((off + 5 * shp[:, 0].long() * shp[:, 1].long()).max()) > stack.numel()):
         raise ValueError("pairs exceed the stack buffer")
     with torch.cuda.device(dev):
         shifts = torch.empty((n, 2), dtype=torch.float64, device=dev)
@@ -148,9 +172,18 @@ def cc_fit_ragged(stack, offsets, shapes, cc_type="NCC", want_icc=False):
         if n == 0:
             return shifts, peak, status, icc, icc_off
         d_off, d_shp = off.to(dev), shp.contiguous().to(dev)
+        if bool(unsupported.any()):
+            bad = torch.nonzero(unsupported).reshape(-1)
+            d_bad = bad.to(dev)
+            shifts[d_bad] = float("nan")
+            peak[d_bad] = -1
+            status[d_bad] = L.S_UNSUPPORTED_SIZE
+            if want_icc:
+                for k in bad.tolist():
+                    icc[int(icc_off[k]):int(icc_off[k + 1])] = float("nan")
         lo = 0
         for cls in _SIZE_CLASSES:
-            idx = torch.nonzero((big > lo) & (big <= cls)).reshape(-1)
+            idx = torch.nonzero((big > lo) & (big <= cls) & ~unsupported).reshape(-1)
             lo = cls
             m = int(idx.numel())
             if m == 0:
@@ -331,7 +364,8 @@ def blot_phases(src, src_offsets, src_shapes, maps, tgt_shapes, phases=PHASES_00
         raise ValueError("between 1 and %d phases" % L.BLOT_MAX_PHASES)
     if n and (int(s_shp.min()) < 1 or int(t_shp.min()) < 1):
         raise ValueError("Cutouts must be 2D images.")
-    if n and int((s_off + s_shp[:, 0].long() * s_shp[:, 1].long()).max()) > src.numel():
+    if n and (int(s_off.min()) < 0 or
+              int((s_off + s_shp[:, 0].long() * s_shp[:, 1].long()).max()) > src.numel()):
         raise ValueError("source cutouts exceed the src buffer")
     sizes = t_shp[:, 0].long() * t_shp[:, 1].long() * nph
     if out is None:

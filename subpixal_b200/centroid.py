@@ -9,6 +9,7 @@ import torch
 
 from . import _lib as L
 from . import batch
+from .utils import native_array
 
 __all__ = ["find_peak"]
 
@@ -44,7 +45,7 @@ def find_peak(image_data, xmax=None, ymax=None, peak_fit_box=5,
     if (xmax is None) != (ymax is None):                     # centroid.py:93-96
         raise ValueError("Both 'xmax' and 'ymax' must be either None or not "
                          "None")
-    img = np.asarray(image_data)
+    img = native_array(image_data)                           # FITS arrays are big-endian
     if img.dtype != np.float32:                              # centroid.py:98
         img = np.asarray(img, dtype=np.float64)
     if img.ndim != 2:

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import batch
+from .utils import native_array
 
 __all__ = ['Cutout', 'create_primary_cutouts', 'create_cutouts',
            'create_input_image_cutouts', 'drz_from_input_cutouts',
@@ -72,18 +73,34 @@ def interpret_bit_flags(flags):
 
 
 def _dq_device_view(arr):
-    """numpy DQ array -> (same-width signed view for torch, original dtype)."""
-    a = np.ascontiguousarray(arr)
+    """numpy DQ array -> (same-width signed view for torch, original dtype).
+    Big-endian arrays (FITS) are converted to native byte order first."""
+    a = native_array(arr)
     if a.dtype.kind not in 'iub':
         raise TypeError("DQ array must have an integer dtype")
     signed = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[a.dtype.itemsize]
     return a.view(signed), a.dtype
 
 
-def _check_float(data):
-    if data.dtype.type not in _FLOATS:
-        raise TypeError("subpixal_b200 cutouts support float32/float64 image "
-                        "data, got %s" % data.dtype)
+def _device_frame(data):
+    """numpy image -> (native float32/float64 array to upload, dtype to restore or None).
+    The reference crops any dtype (cutout.py:737-752: ``np.full(..., dtype=data.dtype)``);
+    the gather kernel reads float32 / float64, so integer, bool and half-precision
+    frames travel as float64 / float32 (exact) and the crops are cast back."""
+    orig = np.asarray(data).dtype
+    a = native_array(data)
+    if a.dtype.type in _FLOATS:
+        return a, (None if orig.isnative else orig)     # crops keep the input dtype
+    if a.dtype.kind in 'iub':
+        if a.dtype.itemsize >= 8 and a.size and \
+                max(abs(int(a.max())), abs(int(a.min()))) > (1 << 53):
+            raise TypeError("subpixal_b200: 64-bit integer image data beyond 2**53 cannot "
+                            "be cropped exactly")
+        return a.astype(np.float64), orig
+    if a.dtype == np.float16:
+        return a.astype(np.float32), orig
+    raise TypeError("subpixal_b200 cutouts support real floating-point and integer image "
+                    "data, got %s" % a.dtype)
 
 
 def _box_checks(nx, ny, blc, trc, mode):
@@ -115,9 +132,9 @@ class _DeviceImage(object):
 
     def __init__(self, data, dq=None, weight=None, seg=None):
         batch.require_cuda()
-        _check_float(data)
+        host, self.restore = _device_frame(data)
         self.shape = data.shape
-        self.data = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+        self.data = torch.from_numpy(host).cuda()
         self.dq = self.dq_dtype = self.weight = self.seg = None
         if dq is not None:
             if dq.shape != data.shape:
@@ -129,18 +146,22 @@ class _DeviceImage(object):
             if weight.shape != data.shape:
                 raise ValueError("Image's weight array shape must match the "
                                  "shape of image 'data'.")
-            w = np.ascontiguousarray(weight)
+            w = native_array(weight)
             if w.dtype.type not in _FLOATS:
                 w = w.astype(np.float64)
             self.weight = torch.from_numpy(w).cuda()
         if seg is not None:
-            s = np.ascontiguousarray(seg)
+            s = native_array(seg)
             if s.dtype not in (np.int32, np.int64):
                 s = s.astype(np.int64)
             self.seg = torch.from_numpy(s).cuda()
 
     def gather(self, boxes, fillval, src_ids=None, dq_good_bits=None):
         """One launch for all boxes; returns per-cutout numpy arrays."""
+        if self.restore is not None:
+            # what numpy stores for ``fillval`` in this dtype (NaN in an integer array
+            # raises here exactly as np.full does in the reference, cutout.py:737)
+            fillval = np.full((), fillval, dtype=self.restore).astype(np.float64)
         res = batch.gather_cutouts(
             self.data, boxes, dq=self.dq, weight=self.weight,
             seg=self.seg if src_ids is not None else None, src_ids=src_ids,
@@ -153,7 +174,8 @@ class _DeviceImage(object):
         for k in range(len(shp)):
             h, w = int(shp[k, 0]), int(shp[k, 1])
             sl = slice(int(off[k]), int(off[k + 1]))
-            item = {"data": flat["data"][sl].reshape(h, w).copy(),
+            item = {"data": (flat["data"][sl].reshape(h, w).copy() if self.restore is None
+                             else flat["data"][sl].reshape(h, w).astype(self.restore)),
                     "mask": flat["mask"][sl].reshape(h, w).astype(np.bool_),
                     "dq": None, "weight": None}
             if "dq" in flat:

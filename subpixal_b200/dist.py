@@ -79,7 +79,9 @@ def frame_displacements_sharded(img_frame, drz_frame, img_boxes, drz_boxes, fram
                                 maps=None, flux_scale=1.0, src_ids=None, **kw):
     """``align.frame_displacements`` (gather + gather + blot + CC, all on the device)
     with the source table sharded by rank; both frames are replicated.  Returns the
-    full ``(shifts, peak, status)`` table on every rank after ONE all-gather."""
+    full ``(shifts, peak, status)`` table on every rank after ONE all-gather.  Keyword
+    arguments (``cc_type``, ``drz_seg``, ``drz_dq``, ``drz_dqbitmask``, ``interp`` ...)
+    are forwarded."""
     import numpy as np
     from . import align
     rank, world = _rank_world(group)

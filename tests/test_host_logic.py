@@ -183,3 +183,47 @@ def test_size_classes_of_the_python_side_match_the_library():
     assert ws(171) > ws(170) + 500000          # 171 px: P = 384
     assert ws(170) - ws(129) < 300000          # inside a class only the surface scratch grows
     assert lib.spx_cc_workspace_bytes(1, L.MAX_CUTOUT + 1, 8, 0) == 0
+
+
+def test_native_array_and_device_frame_conversions():
+    """FITS arrays are big-endian; integer frames are accepted like the
+    reference does (cutout.py:737-752) - host-side conversions only."""
+    from subpixal_b200.utils import native_array
+    from subpixal_b200 import cutout
+    be = np.arange(12, dtype=">f4").reshape(3, 4)
+    nat = native_array(be)
+    assert nat.dtype.isnative and nat.flags.c_contiguous and np.array_equal(nat, be)
+    torch.from_numpy(nat)                                   # would raise on '>f4'
+    host, restore = cutout._device_frame(be)
+    assert host.dtype == np.float32 and host.dtype.isnative and restore == be.dtype
+    host, restore = cutout._device_frame(np.arange(6, dtype=">i2").reshape(2, 3))
+    assert host.dtype == np.float64 and restore == np.dtype(">i2")
+    assert np.array_equal(host, [[0, 1, 2], [3, 4, 5]])
+    host, restore = cutout._device_frame(np.ones((2, 2), dtype=np.float32))
+    assert restore is None
+    with pytest.raises(TypeError):
+        cutout._device_frame(np.full((2, 2), 1 << 60, dtype=np.int64))
+    with pytest.raises(TypeError):
+        cutout._device_frame(np.ones((2, 2), dtype=np.complex64))
+    view, dt = cutout._dq_device_view(np.arange(4, dtype=">u2").reshape(2, 2))
+    assert view.dtype == np.int16 and view.dtype.isnative and dt.isnative
+    torch.from_numpy(view)
+
+
+def test_scratch_cache_release():
+    from subpixal_b200 import batch
+    dev = torch.device("cpu")
+
+    class FakeStream:
+        cuda_stream = 0
+    orig = torch.cuda.current_stream
+    torch.cuda.current_stream = lambda d=None: FakeStream()
+    try:
+        big = batch.scratch_f32("t", 64 << 20, dev)
+        assert batch.scratch_f32("t", 60 << 20, dev) is big          # reused
+        small = batch.scratch_f32("t", 1 << 20, dev)                 # far too large: dropped
+        assert small is not big and small.numel() == 1 << 20
+        batch.clear_scratch()
+        assert not batch._scratch_bufs and not batch._workspaces
+    finally:
+        torch.cuda.current_stream = orig

@@ -5,12 +5,24 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
         --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): 10 000 cutout pairs of 64x64 fp32 taken
+Headline workload (BASELINE.json configs[1]): 10 000 cutout pairs of 64x64 fp32 taken
 from one synthetic 4096x2048 ACS/WFC-like frame (+ the four reference-phase
 frames), cc_type='NCC', full_output=False.  One "step" = one pass of the fused
 gather + cross-correlation + sub-pixel-fit kernel over the 10 000 pairs (per
 GPU; weak scaling), followed for N > 1 by the single NCCL all-gather of the
 shift table.  Prints ONE JSON line on rank 0.
+
+The line also carries a ``sizes`` block - the other half of the metric and
+configs[2] / configs[4]:
+
+* ``"128"``: config 3 - 100 000 pairs 128x128 in stack mode, pixels outside a disc of
+  radius 0.4 N zeroed in the four phase tiles + 0.1 % zeroed phase pixels, NCC and ZNCC;
+* ``"32"``, ``"64"``, ``"256"``: config 5 - 1 M pairs per size in stack mode, cycled over a
+  device-resident pool of >= 8 GB (>> 126 MB of L2);
+
+each with pairs/s, roofline (HBM fraction, ncu DRAM traffic from profiles/), the fp32
+FLOP fraction for the transform size used, and a parity block against the CPU
+reference on the same tiles.
 """
 import argparse
 import json
@@ -29,10 +41,13 @@ UNIT = "pairs/s"
 FRAME_H, FRAME_W = 2048, 4096
 L2_FLUSH_BYTES = 256 << 20
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant
-# kernel, from the committed `ncu --set full` capture (profiles/); None until
-# a capture for the current kernel exists.
-NCU_TRAFFIC_BYTES = {64: 1009666816, 128: None, 32: None}   # profiles/r1_cc_fit_cfg64_ncu_summary.txt
+# fp32 peak of the CUDA cores: 148 SMs x 128 lanes x 2 flop (FMA) x SM clock
+FP32_LANES = 148 * 128
+# flop per pair of the transforms at the alias-free size P = 1.5 N
+MFLOP_PER_PAIR = {32: 0.61, 64: 2.84, 128: 13.0, 256: 58.7}
+# pairs compared with the CPU reference per size
+PARITY_PAIRS = {32: 2000, 64: 2000, 128: 500, 256: 100}
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
 
 def algorithmic_bytes(n):
@@ -49,35 +64,71 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(n, mode, pairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch of
+    ``pairs`` pairs, scaled from the committed ``ncu --set full`` capture of that size
+    class (profiles/ncu_traffic.json names the capture); None when there is none."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            ent = json.load(f)["%d:%s" % (n, mode)]
+        return int(round(ent["dram_bytes_per_pair"] * pairs)), ent["source"]
+    except Exception:
+        return None, None
+
+
 # ----------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference (numpy + scipy.signal.fftconvolve +
-# numpy.linalg.lstsq, exactly the libraries the reference calls) on all host
-# cores.  The unmodified reference is Python and lives in /root/reference,
-# which does not exist on the GPU box, hence kind = "port".
+# CPU arm: the reference's own cc.find_displacement (UNMODIFIED sources, loaded by
+# oracle/refload.py from /root/reference or from the staged copy oracle/_ref made by
+# oracle/make_ref.py) on all host cores - kind "reference"; the oracle port
+# (numpy + scipy.signal.fftconvolve + numpy.linalg.lstsq, the libraries the reference
+# calls) when neither tree is present - kind "port".
 # ----------------------------------------------------------------------------
 _W_STACK = None
+_W_FD = None
+
+
+def cpu_kind():
+    from oracle import refload
+    return "reference" if refload.available() else "port"
 
 
 def _pool_init(path):
-    global _W_STACK
+    global _W_STACK, _W_FD
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["MKL_NUM_THREADS"] = "1"
     import numpy as np
+    from oracle import refload
+    if refload.available():
+        _W_FD = refload.load("cc").find_displacement
+    else:
+        from oracle import subpixal_oracle as orc
+        _W_FD = orc.find_displacement
     _W_STACK = np.load(path, mmap_mode="r")
 
 
-def _pool_work(rng):
+def _pool_work(job):
     import warnings
     import numpy as np
-    from oracle import subpixal_oracle as orc
-    lo, hi = rng
+    lo, hi, cc_type, full = job
     out = []
     with warnings.catch_warnings(), np.errstate(all="ignore"):
         warnings.simplefilter("ignore")
         for k in range(lo, hi):
             st = np.asarray(_W_STACK[k])
-            out.append(orc.find_displacement(st[0], st[1], st[2], st[3], st[4], cc_type="NCC"))
+            if not full:
+                out.append(tuple(float(v) for v in _W_FD(st[0], st[1], st[2], st[3], st[4],
+                                                         cc_type=cc_type)))
+                continue
+            dx, dy, icc, _ = _W_FD(st[0], st[1], st[2], st[3], st[4], cc_type=cc_type,
+                                   full_output=True)
+            flat = icc.ravel().astype(np.float64)
+            am = int(np.argmax(flat))
+            top = flat[am]
+            flat[am] = -np.inf
+            second = float(np.max(flat))
+            tie = bool(top - second <= 1e-5 * abs(top))
+            out.append((float(dx), float(dy), am, tie))
     return out
 
 
@@ -86,18 +137,19 @@ class CpuArm(object):
         import multiprocessing as mp
         import numpy as np
         self.cores = os.cpu_count() or 1
+        self.kind = cpu_kind()
         shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        self.path = os.path.join(shm, "spx_bench_sample_%d.npy" % os.getpid())
+        self.path = os.path.join(shm, "spx_bench_sample_%d_%d.npy" % (os.getpid(), id(self)))
         np.save(self.path, stack)
         self.n = stack.shape[0]
         self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_pool_init,
                                                  initargs=(self.path,))
         self.run(0, min(self.n, 2 * self.cores))          # import + warm caches
 
-    def run(self, lo, hi):
+    def run(self, lo, hi, cc_type="NCC", full=False):
         """Process pairs [lo, hi) on all cores; returns (seconds, results)."""
         chunk = max(1, (hi - lo + 4 * self.cores - 1) // (4 * self.cores))
-        tasks = [(a, min(hi, a + chunk)) for a in range(lo, hi, chunk)]
+        tasks = [(a, min(hi, a + chunk), cc_type, full) for a in range(lo, hi, chunk)]
         t0 = time.perf_counter()
         res = self.pool.map(_pool_work, tasks)
         dt = time.perf_counter() - t0
@@ -110,6 +162,11 @@ class CpuArm(object):
             os.remove(self.path)
         except OSError:
             pass
+
+    def describe(self):
+        return ("unmodified reference cc.find_displacement (oracle/refload.py)"
+                if self.kind == "reference" else
+                "oracle port = numpy + scipy.signal.fftconvolve + numpy.linalg.lstsq")
 
 
 # ----------------------------------------------------------------------------
@@ -177,7 +234,7 @@ def physical_gpu_index(local_rank):
 
 # ----------------------------------------------------------------------------
 def run_reference(args, rank, world, emit):
-    """--impl reference: the reference's CPU path (oracle port) on all host cores."""
+    """--impl reference: the reference's CPU path on all host cores (rank 0 only)."""
     if rank != 0:
         return
     import numpy as np
@@ -207,15 +264,15 @@ def run_reference(args, rank, world, emit):
     finally:
         arm.close()
     value = total_n / total_t
-    sample = "%d pairs of %dx%d per step on %d cores (multiprocessing pool)" % (
-        min(need, per_step), n, n, cores)
+    sample = "%d pairs of %dx%d per step on %d cores (multiprocessing pool; %s)" % (
+        min(need, per_step), n, n, cores, arm.describe())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": arm.kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -237,6 +294,119 @@ def workload_config(args, world):
     }
 
 
+# ----------------------------------------------------------------------------
+# sizes block: configs 3 and 5
+# ----------------------------------------------------------------------------
+SIZE_PLAN = {
+    # size: (config, total pairs per GPU, cc_types, disc mask, zeroed fraction)
+    128: ("config 3: 100k pairs 128x128 with per-cutout masking/normalisation", 100000,
+          ("NCC", "ZNCC"), True, 0.001),
+    32: ("config 5: 1M pairs 32x32 (stack mode, pool cycled)", 1000000, ("NCC",), False, 0.0),
+    64: ("config 5: 1M pairs 64x64 (stack mode, pool cycled)", 1000000, ("NCC",), False, 0.0),
+    256: ("config 5: 1M pairs 256x256 (stack mode, pool cycled)", 1000000, ("NCC",), False, 0.0),
+}
+
+
+def bench_size(n, args, rank, world, dev, get_gather, sm_mhz):
+    """One entry of the ``sizes`` block (every rank takes part; rank 0 returns the dict)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from subpixal_b200 import batch, synthetic as syn
+    label, total, cc_types, disc, zfrac = SIZE_PLAN[n]
+    total = max(1, int(total * args.sizes_scale))
+    bpp = algorithmic_bytes(n)
+    pool_pairs = int(min(total, max(PARITY_PAIRS[n], -(-args.pool_bytes // bpp))))
+    stack, _ = syn.make_pair_pool(pool_pairs, n, args.seed + 1000 * n + rank, dev,
+                                  disc_mask=disc, zero_frac=zfrac)
+    launches = -(-total // pool_pairs)              # the pool is cycled until `total` pairs
+    done = launches * pool_pairs
+    peak, peak_src = measured_peak()
+    entry = {"config": label, "mode": "stack [n,5,N,N], device resident",
+             "pairs_per_gpu": done, "pool_pairs": pool_pairs,
+             "pool_bytes": int(stack.numel() * 4), "launches_per_pass": launches,
+             "l2": "pool >> 126 MB L2: every launch streams its inputs from HBM",
+             "masking": ("phase tiles zero outside a disc of radius 0.4 N + %.1f %% zeroed "
+                         "phase pixels" % (100 * zfrac)) if disc else "none",
+             "cc": {}}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in cc_types:
+        out = None
+        for _ in range(2):                                       # warm-up launches
+            out = batch.cc_fit_stack(stack[:min(pool_pairs, 4096)], t)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        g = get_gather(pool_pairs) if world > 1 else None
+        for _ in range(launches):
+            # N > 1: the kernel writes this rank's packed result rows into the persistent
+            # send buffer, one all-gather returns the full table to every rank
+            out = batch.cc_fit_stack(stack, t, table=g.local if g else None)
+            if g:
+                g.gather()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        rate = world * done / (ms / 1e3)
+        per_gpu = rate / world
+        achieved = per_gpu * bpp / 1e9
+        traffic, tsrc = ncu_traffic(n, "stack", pool_pairs)
+        flop = MFLOP_PER_PAIR[n] * 1e6
+        fp32_peak = FP32_LANES * 2 * (sm_mhz or 1965.0) * 1e6
+        res = {"pairs_per_s": rate, "ms_per_launch": ms / launches,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
+                            "kernel": "cc_fit_kernel<Cfg%d>" % n, "bytes_per_pair": bpp,
+                            "pairs_per_launch": pool_pairs, "peak_source": peak_src},
+               "fp32_flop_frac": per_gpu * flop / fp32_peak,
+               "fp32": {"mflop_per_pair": MFLOP_PER_PAIR[n], "transform_size": 3 * n // 2,
+                        "peak_tflops": fp32_peak / 1e12,
+                        "peak_formula": "148 SMs x 128 lanes x 2 x %.0f MHz" % (sm_mhz or 1965.0)}}
+        # ---- parity against the CPU reference on the SAME tiles (rank 0) ----------
+        if rank == 0 and not args.no_cpu_baseline:
+            m = min(pool_pairs, PARITY_PAIRS[n])
+            host = stack[:m].cpu().numpy()
+            sh = out[0][:m].cpu().numpy()
+            pk = out[1][:m].cpu().numpy()
+            arm = CpuArm(host)
+            try:
+                dt, ref = arm.run(0, m, cc_type=t, full=True)
+            finally:
+                arm.close()
+            rdx = np.array([[r[0], r[1]] for r in ref])
+            ram = np.array([r[2] for r in ref])
+            tie = np.array([r[3] for r in ref])
+            same = ram == pk
+            diff = np.abs(sh - rdx)
+            res["parity"] = {
+                "n_compared": int(m), "against": arm.kind,
+                "max_abs_shift_diff": float(diff[same].max()) if same.any() else None,
+                "argmax_mismatches": int((~same).sum()),
+                "argmax_mismatches_not_near_tie": int((~same & ~tie).sum()),
+                "near_tie_rate": float(tie.mean()),
+                "tolerance_px": 1e-3,
+                "ok": bool((~same & ~tie).sum() == 0 and
+                           (not same.any() or float(diff[same].max()) < 1e-3)),
+                "cpu_pairs_per_s": m / dt, "cpu_cores": arm.cores}
+        entry["cc"][t] = res
+    first = entry["cc"][cc_types[0]]
+    for k in ("pairs_per_s", "roofline", "fp32_flop_frac", "parity"):
+        if k in first:
+            entry[k] = first[k]                     # the NCC figures at the top level
+    del stack
+    torch.cuda.empty_cache()
+    return entry
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -249,6 +419,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-pairs-per-core", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sizes", default="128,32,64,256",
+                    help="comma-separated sizes of the `sizes` block ('' = none)")
+    ap.add_argument("--sizes-scale", type=float, default=1.0,
+                    help="scale the pairs per size (1.0 = the BASELINE.json counts)")
+    ap.add_argument("--pool-bytes", type=int, default=8 << 30)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -292,13 +467,24 @@ def main():
     boxes_np = syn.make_boxes(sc)
     boxes = torch.from_numpy(boxes_np).to(dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    _, _, per = sdist.shard_range(npairs * world, rank, world)
+    gatherers = {}
 
-    def step_device():
-        sh, pk, st, _ = batch.cc_fit_frames(frames, boxes, n, n, "NCC")
+    def get_gather(per):
+        """Persistent send / receive buffers of the ONE collective of the path (the
+        all-gather of the per-rank result table), one set per table length."""
+        g = gatherers.get(per)
+        if g is None:
+            g = gatherers[per] = sdist.ResultGather(per, world, dev)
+        return g
+
+    def step_device(fr=None, bx=None):
+        fr, bx = (frames, boxes) if fr is None else (fr, bx)
         if world > 1:
-            return sdist.allgather_results(sdist.pack_results(sh, pk, st, per), npairs * world)
-        return sh, pk, st
+            g = get_gather(npairs)
+            batch.cc_fit_frames(fr, bx, n, n, "NCC", table=g.local)    # packed rows, no glue
+            return g.gather()
+        out = batch.cc_fit_frames(fr, bx, n, n, "NCC")
+        return out[0], out[1], out[2]
 
     def barrier():
         if world > 1:
@@ -356,10 +542,7 @@ def main():
         d_fr, d_bx, h_out = bufs[i % 2]
         with torch.cuda.stream(s_comp):
             s_comp.wait_event(up_done[i % 2])
-            sh, pk, st, _ = batch.cc_fit_frames(d_fr, d_bx, n, n, "NCC")
-            if world > 1:
-                sh, pk, st = sdist.allgather_results(sdist.pack_results(sh, pk, st, per),
-                                                     npairs * world)
+            sh = step_device(d_fr, d_bx)[0]
             h_out.copy_(sh, non_blocking=True)
             buf_free[i % 2].record(s_comp)
         return h_out
@@ -390,23 +573,31 @@ def main():
     e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 0.0)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * npairs * e2e_steps / (float(e2e_ms.item()) / 1e3)
+    e2e_ms = float(e2e_ms.item())
+    e2e_value = world * npairs * e2e_steps / (e2e_ms / 1e3)
     h2d = int(h_frames.numel() * 4 + h_boxes.numel() * 4)
     d2h = int(n_out * 16)
+    h2d_gbs_rank = h2d * e2e_steps / (e2e_ms / 1e3) / 1e9
+    del h_frames, bufs
 
     # ---- roofline of the dominant kernel (rank 0's own launches) ----------
     peak, peak_src = measured_peak()
     kern_ms = statistics.mean(ms_steps)
     achieved = npairs * algorithmic_bytes(n) / (kern_ms / 1e3) / 1e9
+    traffic, traffic_src = ncu_traffic(n, "frames", npairs)
+    sm_mhz = (clocks or {}).get("sm_mhz")
+    fp32_peak = FP32_LANES * 2 * (sm_mhz or 1965.0) * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(n),
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "cc_fit_kernel<Cfg%d>" % n, "peak_source": peak_src,
                 "bytes_per_pair": algorithmic_bytes(n), "pairs_per_launch": npairs,
                 "launch_ms": kern_ms,
+                "fp32_flop_frac": (npairs / (kern_ms / 1e3)) * MFLOP_PER_PAIR.get(n, 0.0) * 1e6
+                / fp32_peak,
                 "note": "HBM fraction as BASELINE.json defines it; the kernel is bound by fp32 "
                         "issue / shared-memory bandwidth (SURVEY.md section 8d), see DESIGN.md"}
 
-    # ---- CPU baseline: the oracle port on this box's host cores (rank 0, N=1) ----
+    # ---- CPU baseline: the reference on this box's host cores (rank 0, N=1) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -426,12 +617,22 @@ def main():
         # the same pairs on the GPU: parity of the benchmarked configuration
         sh = step_device()[0][:want].cpu().numpy()
         ref = np.array(res)
-        cpu = {"value": m / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": m / dt, "unit": UNIT, "cores": cores, "kind": arm.kind,
                "sample": "first %d of the %d pairs, %d passes = %d pairs in %.1f s wall "
-                         "(multiprocessing pool on all cores; oracle = numpy + "
-                         "scipy.signal.fftconvolve + numpy.linalg.lstsq)"
-                         % (want, npairs, passes, m, dt),
+                         "(multiprocessing pool on all cores; %s)"
+                         % (want, npairs, passes, m, dt, arm.describe()),
                "max_abs_shift_diff_vs_gpu_px": float(np.max(np.abs(sh - ref)))}
+
+    # ---- the other sizes of the metric: configs 3 and 5 --------------------------
+    sizes = {}
+    del frames
+    torch.cuda.empty_cache()
+    for s in [int(v) for v in args.sizes.split(",") if v.strip()]:
+        if s not in SIZE_PLAN:
+            continue
+        entry = bench_size(s, args, rank, world, dev, get_gather, sm_mhz)
+        if rank == 0:
+            sizes[str(s)] = entry
 
     if rank == 0:
         line = {
@@ -443,11 +644,18 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "wall_ms_per_step": wall_ms / e2e_steps,
+                    "h2d_gbs_per_rank": h2d_gbs_rank,
+                    "limiter": "host->device copy of the five frames (168 MB per step and rank) "
+                               "over PCIe: %.1f GB/s per rank, %.0f GB/s for the %d ranks of this "
+                               "host; the kernel needs %.2f ms of the %.2f ms step"
+                               % (h2d_gbs_rank, h2d_gbs_rank * world, world, kern_ms,
+                                  e2e_ms / e2e_steps),
                     "note": "pinned host -> device copy of the 5 frames + boxes and device -> "
                             "host copy of the shifts every step; upload of step i+1 overlaps "
                             "the kernel of step i (two buffer sets, two streams)"},
             "gpu_launches": args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "sizes": sizes,
         }
         emit(line)
     if world > 1:

@@ -132,6 +132,12 @@ int spx_gather_cutouts(const spx_gather_args *args_host, void *stream);
  * status     [n] int32 SPX_S_* bits
  * icc        [n,2ny,2nx] float32 or NULL (full_output, cc.py:95,128)
  * workspace  spx_cc_workspace_bytes(...) bytes, 256-byte aligned
+ *
+ * Packed output (all three spx_cc_fit_* entry points): when `peak` and
+ * `status` are BOTH NULL, `shifts` is an [n,4] float64 table and pair p gets
+ * the row (dx, dy, peak, status) - the per-rank block that the multi-GPU path
+ * sends with its single all-gather (align.py:689 collects exactly this table),
+ * written by the kernel itself so that no packing kernels run per step.
  * ======================================================================== */
 size_t spx_cc_workspace_bytes(int n, int ny, int nx, int want_icc);
 

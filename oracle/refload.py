@@ -12,7 +12,8 @@ numpy >= 1.24).  The hot-path files themselves (``utils.py``, ``centroid.py``,
 ``cc.py``, ``cutout.py``) only *use* numpy and scipy, so we execute them by
 path with stub modules registered for the missing imports (recipe of
 SURVEY.md section 8c).  ``/root/reference`` only exists in the build
-container, so ``available()`` must be checked first; on the GPU box the
+container, so ``available()`` must be checked first; on the GPU box the staged
+copy ``oracle/_ref/`` (made by ``oracle/make_ref.py``, git-ignored) and the
 committed fixtures under ``tests/golden/`` stand in for it.
 """
 import importlib.util
@@ -23,12 +24,22 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get("SUBPIXAL_REFERENCE", "/root/reference")
+# byte-for-byte staging copy made by oracle/make_ref.py (git-ignored; travels to the GPU box)
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _PKG = "subpixal"
 _cache = {}
 
 
+def root():
+    """Directory holding ``subpixal/``: the mounted reference tree, else the staged copy."""
+    for r in (REFERENCE_ROOT, STAGED_ROOT):
+        if os.path.isfile(os.path.join(r, _PKG, "cc.py")):
+            return r
+    return None
+
+
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, _PKG, "cc.py"))
+    return root() is not None
 
 
 def _bitfield_to_boolean_mask(bitfield, ignore_flags=0, flip_bits=None,
@@ -43,6 +54,12 @@ def _bitfield_to_boolean_mask(bitfield, ignore_flags=0, flip_bits=None,
         ignore = int(ignore_flags)
         bad = (bitfield & ~np.array(ignore, dtype=bitfield.dtype)) != 0
     return (~bad if good_mask_value else bad).astype(dtype)
+
+
+def _proj_plane_pixel_area(wcs):
+    """Stand-in for astropy.wcs.utils.proj_plane_pixel_area (un-vendored; used by
+    Cutout.pscale, cutout.py:1153-1157): |det| of the WCS's pixel scale matrix."""
+    return abs(float(np.linalg.det(np.asarray(wcs.pixel_scale_matrix, dtype=np.float64))))
 
 
 def _install_stubs():
@@ -60,6 +77,7 @@ def _install_stubs():
         a.io = mod("astropy.io")
         a.io.fits = mod("astropy.io.fits")
         a.wcs = mod("astropy.wcs")
+        a.wcs.utils = mod("astropy.wcs.utils", proj_plane_pixel_area=_proj_plane_pixel_area)
     if "stwcs" not in sys.modules:
         s = mod("stwcs")
         s.wcsutil = mod("stwcs.wcsutil", HSTWCS=object)
@@ -70,7 +88,7 @@ def _install_stubs():
             "stsci.tools.bitmask",
             bitfield_to_boolean_mask=_bitfield_to_boolean_mask)
     pkg = mod(_PKG, __version__="reference", __version_date__="n/a")
-    pkg.__path__ = [os.path.join(REFERENCE_ROOT, _PKG)]
+    pkg.__path__ = [os.path.join(root(), _PKG)]
     mod(_PKG + ".catalogs", ImageCatalog=type("ImageCatalog", (), {}))
     if not hasattr(np, "bool"):
         np.bool = bool  # cc.py:150
@@ -82,14 +100,15 @@ def load(name):
     if name in _cache:
         return _cache[name]
     if not available():
-        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+        raise RuntimeError("reference tree not present at %s nor staged in %s"
+                           % (REFERENCE_ROOT, STAGED_ROOT))
     _install_stubs()
     for dep in {"centroid": ["utils"], "cc": ["utils", "centroid"],
                 "cutout": []}.get(name, []):
         load(dep)
     full = _PKG + "." + name
     spec = importlib.util.spec_from_file_location(
-        full, os.path.join(REFERENCE_ROOT, _PKG, name + ".py"))
+        full, os.path.join(root(), _PKG, name + ".py"))
     m = importlib.util.module_from_spec(spec)
     sys.modules[full] = m
     spec.loader.exec_module(m)

@@ -90,20 +90,39 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-def _outputs(n, ny, nx, want_icc, device):
-    shifts = torch.empty((n, 2), dtype=torch.float64, device=device)
-    peak = torch.empty((n,), dtype=torch.int32, device=device)
-    status = torch.empty((n,), dtype=torch.int32, device=device)
+def _outputs(n, ny, nx, want_icc, device, table=None):
+    """Output tensors of a cc_fit call.  With ``table`` (a caller-owned ``[>= n, 4]``
+    float64 CUDA tensor, e.g. the persistent send buffer of ``dist.ResultGather``) the
+    kernel writes the packed rows (dx, dy, peak, status) itself and the returned
+    shifts / peak / status are float64 VIEWS of its first n rows."""
+    if table is not None:
+        if (table.dtype != torch.float64 or table.dim() != 2 or table.shape[1] != 4 or
+                table.shape[0] < n or not table.is_contiguous() or table.device != device):
+            raise ValueError("table must be a contiguous [>= n, 4] float64 tensor on the device")
+        shifts, peak, status = table[:n, :2], table[:n, 2], table[:n, 3]
+    else:
+        shifts = torch.empty((n, 2), dtype=torch.float64, device=device)
+        peak = torch.empty((n,), dtype=torch.int32, device=device)
+        status = torch.empty((n,), dtype=torch.int32, device=device)
     icc = (torch.empty((n, 2 * ny, 2 * nx), dtype=torch.float32, device=device)
            if want_icc else None)
     return shifts, peak, status, icc
 
 
-def cc_fit_stack(stack, cc_type="NCC", want_icc=False):
+def _out_ptrs(shifts, peak, status, table):
+    """(shifts, peak, status) pointers of the C ABI; peak = status = NULL selects the
+    packed table form."""
+    if table is not None:
+        return _ptr(table), C.c_void_p(0), C.c_void_p(0)
+    return _ptr(shifts), _ptr(peak), _ptr(status)
+
+
+def cc_fit_stack(stack, cc_type="NCC", want_icc=False, table=None):
     """Cross-correlate + fit n pairs stored as a ``[n, 5, ny, nx]`` float32
     stack (slot 0 = ref_image, 1..4 = image00, image10, image01, image11).
     Returns ``(shifts [n,2] f64, peak [n] i32, status [n] i32, icc or None)``.
-    Batched form of cc.find_displacement (reference cc.py:21-95)."""
+    Batched form of cc.find_displacement (reference cc.py:21-95).  ``table``: see
+    ``_outputs`` (packed [n,4] float64 result rows written by the kernel)."""
     require_cuda()
     lib = L.load()
     stack = _f32c(stack, "stack")
@@ -112,7 +131,7 @@ def cc_fit_stack(stack, cc_type="NCC", want_icc=False):
     n, _, ny, nx = (int(v) for v in stack.shape)
     dev = stack.device
     with torch.cuda.device(dev):
-        shifts, peak, status, icc = _outputs(n, ny, nx, want_icc, dev)
+        shifts, peak, status, icc = _outputs(n, ny, nx, want_icc, dev, table)
         if n == 0:
             return shifts, peak, status, icc
         nb = lib.spx_cc_workspace_bytes(n, ny, nx, int(want_icc))
@@ -122,7 +141,7 @@ def cc_fit_stack(stack, cc_type="NCC", want_icc=False):
         strides = (C.c_int64 * 5)(*([5 * tile] * 5))
         L.check(lib.spx_cc_fit_stack(
             *(C.c_void_p(base + 4 * tile * s) for s in range(5)), C.byref(strides),
-            n, ny, nx, cc_type_code(cc_type), _ptr(shifts), _ptr(peak), _ptr(status),
+            n, ny, nx, cc_type_code(cc_type), *_out_ptrs(shifts, peak, status, table),
             _ptr(icc), _ptr(ws), ws.numel(), _stream()))
     return shifts, peak, status, icc
 
@@ -200,7 +219,7 @@ def cc_fit_ragged(stack, offsets, shapes, cc_type="NCC", want_icc=False):
 
 
 def cc_fit_frames(frames, boxes, ny, nx, cc_type="NCC", want_icc=False,
-                  zero_bad_phases=True, zero_bad_ref=False):
+                  zero_bad_phases=True, zero_bad_ref=False, table=None):
     """Fused gather + cross-correlation + fit straight from five full frames
     (``frames[0]`` = image frame, ``frames[1..4]`` = reference frames at the
     four half-pixel phases; a ``[5, H, W]`` tensor or a sequence of five
@@ -220,7 +239,7 @@ def cc_fit_frames(frames, boxes, ny, nx, cc_type="NCC", want_icc=False,
     flags = (L.F_ZERO_BAD_PHASES if zero_bad_phases else 0) | \
             (L.F_ZERO_BAD_REF if zero_bad_ref else 0)
     with torch.cuda.device(dev):
-        shifts, peak, status, icc = _outputs(n, ny, nx, want_icc, dev)
+        shifts, peak, status, icc = _outputs(n, ny, nx, want_icc, dev, table)
         if n == 0:
             return shifts, peak, status, icc
         nb = lib.spx_cc_workspace_bytes(n, ny, nx, int(want_icc))
@@ -228,7 +247,7 @@ def cc_fit_frames(frames, boxes, ny, nx, cc_type="NCC", want_icc=False,
         ptrs = (C.c_void_p * 5)(*(f.data_ptr() for f in fr))
         L.check(lib.spx_cc_fit_frames(
             C.byref(ptrs), H, W, W, _ptr(boxes), n, int(ny), int(nx),
-            cc_type_code(cc_type), flags, _ptr(shifts), _ptr(peak), _ptr(status),
+            cc_type_code(cc_type), flags, *_out_ptrs(shifts, peak, status, table),
             _ptr(icc), _ptr(ws), ws.numel(), _stream()))
     return shifts, peak, status, icc
 

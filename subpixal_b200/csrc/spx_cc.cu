@@ -352,7 +352,11 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
         job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
         if (rank == 0) prefetch_pair<C>(prm, k + nunits, pfmap);
-        process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
+        // peak == NULL: packed [n,4] float64 result table (dx, dy, peak, status)
+        if (prm.peak)
+            process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
+        else
+            process_pair<C>(c, ex, job, prm.shifts + 4 * size_t(p), nullptr, nullptr);
     }
     if (C::CL == 2) cg::this_cluster().sync();     // do not exit while the peer may still read my W
 }
@@ -462,7 +466,8 @@ static int launch(CcParams &prm, const SlabPlan &sp, cudaStream_t stream) {
 }
 
 static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *stream) {
-    if (prm.n < 0 || !prm.shifts || !prm.peak || !prm.status) return SPX_E_BADARG;
+    // peak and status both NULL: `shifts` is the packed [n,4] float64 table
+    if (prm.n < 0 || !prm.shifts || (!prm.peak) != (!prm.status)) return SPX_E_BADARG;
     for (int s = 0; s < 5; ++s) if (!prm.src[s]) return SPX_E_BADARG;
     if (prm.ny < SPX_MIN_CUTOUT || prm.nx < SPX_MIN_CUTOUT) return SPX_E_UNSUPPORTED;
     const int cfg = pick_cfg(prm.ny, prm.nx);

@@ -838,7 +838,14 @@ SPX_HD void peak_final(const PairState &ps, const PeakGeom &g, const FitSums &f,
     const int xc4 = (w2 - 1) / 4, yc4 = (h2 - 1) / 4;                   // cc.py:89-90
     shift2[0] = 0.5 * x - double(xc4);                                   // cc.py:92-93
     shift2[1] = 0.5 * y - double(yc4);
-    *peak = g.idx;
+    if (peak) {
+        *peak = g.idx;
+    } else {
+        // packed result table (dx, dy, peak, status) as four doubles: the row the
+        // multi-GPU all-gather sends (ints up to 2^31 are exact in float64)
+        shift2[2] = double(g.idx);
+        shift2[3] = double(st & ~kSawNonFinite);
+    }
     *status = st & ~kSawNonFinite;
 }
 
@@ -1048,7 +1055,7 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
                 const PeakGeom g = peak_geometry(*ps);
                 int st;
                 peak_final(*ps, g, f, shift2, peak, &st);
-                *status = st;
+                if (status) *status = st;
                 ps->status = st;
             });
     }

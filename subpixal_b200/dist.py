@@ -11,8 +11,8 @@ gloo (CPU tests of the host logic).
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "pack_results", "allgather_results", "cc_fit_frames_sharded",
-           "cc_fit_stack_sharded", "frame_displacements_sharded"]
+__all__ = ["shard_range", "pack_results", "allgather_results", "ResultGather",
+           "cc_fit_frames_sharded", "cc_fit_stack_sharded", "frame_displacements_sharded"]
 
 
 def shard_range(n, rank, world):
@@ -48,6 +48,41 @@ def allgather_results(table, n, group=None):
     return full[:, :2].contiguous(), full[:, 2].to(torch.int64), full[:, 3].to(torch.int64)
 
 
+class ResultGather(object):
+    """Persistent buffers for the ONE collective of the path: the kernel writes this
+    rank's packed rows (dx, dy, peak, status; float64) straight into ``self.local``
+    (``batch.cc_fit_*(..., table=gather.local)``), ``gather()`` sends them with one
+    ``all_gather_into_tensor`` into ``self.full`` and returns VIEWS of it - no packing
+    or unpacking kernels, no allocation per step.  Rows past a rank's own pair count
+    keep the NaN / -1 padding they were created with."""
+
+    def __init__(self, per_rank, world, device, group=None):
+        self.per, self.world, self.group = int(per_rank), int(world), group
+        self.local = torch.empty((self.per, 4), dtype=torch.float64, device=device)
+        self.local[:, :2] = float("nan")
+        self.local[:, 2:] = -1.0
+        self.full = (torch.empty((self.world * self.per, 4), dtype=torch.float64, device=device)
+                     if self.world > 1 else self.local)
+
+    def gather(self, n=None):
+        """All-gather ``self.local``; returns float64 views ``(shifts [n,2], peak [n],
+        status [n])`` of the gathered table (peak / status hold exact integers)."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.full, self.local, group=self.group)
+        n = self.full.shape[0] if n is None else n
+        return self.full[:n, :2], self.full[:n, 2], self.full[:n, 3]
+
+    def __call__(self, shifts, peak, status):
+        """Results that were NOT written through ``table=self.local`` (separate tensors):
+        copy them into the send buffer, then gather."""
+        m = shifts.shape[0]
+        if shifts.data_ptr() != self.local.data_ptr():
+            self.local[:m, :2] = shifts
+            self.local[:m, 2] = peak
+            self.local[:m, 3] = status
+        return self.gather()
+
+
 def _rank_world(group=None):
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -61,8 +96,10 @@ def cc_fit_frames_sharded(frames, boxes, ny, nx, cc_type="NCC", group=None, **kw
     rank, world = _rank_world(group)
     n = int(boxes.shape[0])
     lo, hi, per = shard_range(n, rank, world)
-    sh, pk, st, _ = batch.cc_fit_frames(frames, boxes[lo:hi], ny, nx, cc_type, **kw)
-    return allgather_results(pack_results(sh, pk, st, per), n, group)
+    g = ResultGather(per, world, boxes.device if boxes.is_cuda else frames[0].device, group)
+    batch.cc_fit_frames(frames, boxes[lo:hi], ny, nx, cc_type, table=g.local, **kw)
+    sh, pk, st = g.gather(n)
+    return sh.contiguous(), pk.to(torch.int64), st.to(torch.int64)
 
 
 def cc_fit_stack_sharded(local_stack, n_total, cc_type="NCC", group=None):
@@ -71,8 +108,10 @@ def cc_fit_stack_sharded(local_stack, n_total, cc_type="NCC", group=None):
     from . import batch
     rank, world = _rank_world(group)
     _, _, per = shard_range(n_total, rank, world)
-    sh, pk, st, _ = batch.cc_fit_stack(local_stack, cc_type)
-    return allgather_results(pack_results(sh, pk, st, per), n_total, group)
+    g = ResultGather(per, world, local_stack.device, group)
+    batch.cc_fit_stack(local_stack, cc_type, table=g.local)
+    sh, pk, st = g.gather(n_total)
+    return sh.contiguous(), pk.to(torch.int64), st.to(torch.int64)
 
 
 def frame_displacements_sharded(img_frame, drz_frame, img_boxes, drz_boxes, frame_map, group=None,

@@ -98,3 +98,58 @@ def cut_stack(frames_np, boxes):
     for k, (x1, y1, x2, y2) in enumerate(boxes):
         out[k] = frames_np[:, y1:y2 + 1, x1:x2 + 1]
     return out
+
+
+def make_pair_pool(n_pairs, n, seed, device, disc_mask=False, zero_frac=0.0, chunk=None):
+    """``[n_pairs, 5, n, n]`` float32 stack of synthetic cutout pairs generated on the
+    device: per pair one elliptical Gaussian
+    source near the cutout centre plus a fainter neighbour, unit read noise in the image
+    tile (slot 0), noise-free reference tiles at the four half-pixel phases (slots 1..4)
+    displaced by a per-pair true shift around (0.37, -0.21) px.
+
+    ``disc_mask``: pixels outside a disc of radius 0.4 n around the source are 0 in the
+    four phase tiles (segmentation mask + align.py:661); ``zero_frac``: that fraction of
+    random phase pixels is 0 as well (the NaN pixels the gather masks and zeroes,
+    cutout.py:755 + align.py:661).  Returns ``(stack, truth [n_pairs, 2])``."""
+    gen = torch.Generator(device=device).manual_seed(int(seed))
+    stack = torch.empty((n_pairs, 5, n, n), dtype=torch.float32, device=device)
+    truth = torch.empty((n_pairs, 2), dtype=torch.float64, device=device)
+    if chunk is None:
+        chunk = max(1, (1 << 25) // (n * n))
+    ax = torch.arange(n, device=device, dtype=torch.float32)
+    yy, xx = ax[None, :, None], ax[None, None, :]
+    c = (n - 1) / 2.0
+    u = lambda m, lo, hi: lo + (hi - lo) * torch.rand((m, 1, 1), generator=gen, device=device)
+
+    def blob(x0, y0, sig, q, pa, amp):
+        dx, dy = xx - x0, yy - y0
+        cs, sn = torch.cos(pa), torch.sin(pa)
+        a, b = cs * dx + sn * dy, -sn * dx + cs * dy
+        return amp * torch.exp(-(a * a / (2 * sig * sig) + b * b / (2 * (sig * q) ** 2)))
+
+    for lo in range(0, n_pairs, chunk):
+        m = min(chunk, n_pairs - lo)
+        x0, y0 = c + u(m, -2.5, 2.5), c + u(m, -2.5, 2.5)
+        src = (u(m, 1.5, 4.0), u(m, 0.5, 1.0), u(m, 0.0, math.pi),
+               torch.exp(u(m, math.log(50.0), math.log(5000.0))))
+        # a fainter neighbour somewhere in the cutout, moving coherently with the source
+        x1, y1 = u(m, 0.15 * n, 0.85 * n), u(m, 0.15 * n, 0.85 * n)
+        nb = (u(m, 1.5, 3.0), u(m, 0.6, 1.0), u(m, 0.0, math.pi), src[3] * u(m, 0.02, 0.2))
+        sx, sy = 0.37 + u(m, -0.1, 0.1), -0.21 + u(m, -0.1, 0.1)
+        out = stack[lo:lo + m]
+        out[:, 0] = blob(x0, y0, *src) + blob(x1, y1, *nb) + \
+            torch.randn((m, n, n), generator=gen, device=device)
+        keep = None
+        if disc_mask:
+            keep = ((xx - x0) ** 2 + (yy - y0) ** 2) <= (0.4 * n) ** 2
+        for k, (a, b) in enumerate(PHASES):
+            ph = blob(x0 + sx - a / 2.0, y0 + sy - b / 2.0, *src) + \
+                blob(x1 + sx - a / 2.0, y1 + sy - b / 2.0, *nb)
+            if keep is not None:
+                ph = ph * keep
+            if zero_frac > 0.0:
+                ph = ph * (torch.rand((m, n, n), generator=gen, device=device) >= zero_frac)
+            out[:, 1 + k] = ph
+        truth[lo:lo + m, 0] = sx.reshape(-1).double()
+        truth[lo:lo + m, 1] = sy.reshape(-1).double()
+    return stack, truth

@@ -193,6 +193,27 @@ def cutout_cases(ct):
     np.savez_compressed(os.path.join(HERE, "cutout.npz"), **out)
 
 
+def builder_cases(ct):
+    """The reference's OWN list builders (cutout.py:47-198, 201-306, 309-438, 441-587)
+    on the scenes of tests/wcs_stubs.py: boxes, masks, source positions, list order
+    and the dropped sources are frozen for the product's builders to match exactly."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import wcs_stubs as ws
+    out = {}
+    for seed in (20280, 20281):
+        sc = ws.builder_scene(seed)
+        for name, pkw, ckw in ws.BUILDER_CASES:
+            if not ws.case_in_fixture(seed, name):
+                continue
+            prim, flt_cts, drz_cts = ws.run_builders(ct, sc, pkw, ckw)
+            tag = "s%d_%s" % (seed, name)
+            ws.pack_cutouts(tag + "_prim", prim, out)
+            ws.pack_cutouts(tag + "_flt", flt_cts, out)
+            ws.pack_cutouts(tag + "_drz", drz_cts, out)
+            out[tag + "_pscale"] = np.array([flt_cts[0].pscale, drz_cts[0].pscale])
+    np.savez_compressed(os.path.join(HERE, "builders.npz"), **out)
+
+
 def main():
     if not refload.available():
         raise SystemExit("reference tree not mounted; fixtures unchanged")
@@ -202,6 +223,7 @@ def main():
     degenerate(cc)
     peak_cases(ce)
     cutout_cases(ct)
+    builder_cases(ct)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

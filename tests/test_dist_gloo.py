@@ -25,6 +25,21 @@ def _worker(rank, world, port, n):
         assert torch.equal(pk, torch.arange(n) * 3)
         owner = torch.clamp(torch.arange(n) // per, max=world - 1)
         assert torch.equal(st, owner)
+        # persistent-buffer form: the producer writes packed rows into g.local (what the
+        # kernel does with table=g.local), one all-gather, views come back
+        g = d.ResultGather(per, world, torch.device("cpu"))
+        assert torch.isnan(g.local[:, :2]).all() and bool((g.local[:, 2:] == -1).all())
+        g.local[:hi - lo, :2] = shifts
+        g.local[:hi - lo, 2] = peak
+        g.local[:hi - lo, 3] = status
+        for _ in range(2):                                   # buffers are reused
+            sh2, pk2, st2 = g.gather(n)
+            assert torch.equal(sh2, sh) and torch.equal(pk2.long(), pk) and torch.equal(st2.long(), st)
+            assert sh2.data_ptr() == g.full.data_ptr()       # a view, nothing unpacked
+        if n % world:                                         # the tail keeps its padding
+            assert torch.isnan(g.full[n:, :2]).all()
+        sh3, _, _ = g(shifts, peak, status)                   # separate tensors -> copied in
+        assert torch.equal(sh3[:n], sh)
     finally:
         dist.destroy_process_group()
 

@@ -162,3 +162,23 @@ def test_live_against_reference():
     dq = rng.integers(0, 64, size=(4, 4)).astype(np.int32)
     ref_bad = refload._bitfield_to_boolean_mask(dq, 6, good_mask_value=False)
     assert np.array_equal(ref_bad, orc.bitfield_bad_mask(dq, 6))
+
+
+@pytest.mark.skipif(not refload.available(),
+                    reason="/root/reference only exists in the build container")
+def test_builder_fixture_is_what_the_reference_produces():
+    """tests/golden/builders.npz = outputs of the reference's own create_primary_cutouts /
+    create_cutouts (cutout.py:47-587) on the scenes of tests/wcs_stubs.py, re-run live."""
+    import wcs_stubs as ws
+    ct = refload.load("cutout")
+    g = golden("builders")
+    seed = ws.BUILDER_SEEDS[1]
+    for name, pkw, ckw in ws.BUILDER_CASES:
+        if not ws.case_in_fixture(seed, name):
+            continue
+        out = {}
+        prim, flt_cts, drz_cts = ws.run_builders(ct, ws.builder_scene(seed), pkw, ckw)
+        tag = "s%d_%s" % (seed, name)
+        for suffix, cts in (("_prim", prim), ("_flt", flt_cts), ("_drz", drz_cts)):
+            ws.pack_cutouts(tag + suffix, cts, out)
+        assert out and all(np.array_equal(v, g[k], equal_nan=True) for k, v in out.items())

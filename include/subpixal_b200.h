@@ -52,6 +52,11 @@ extern "C" {
                                       set to 0 (align.py:661 + cutout.py:755) */
 #define SPX_F_ZERO_BAD_REF    0x2u /* same for the image ("ref_image") frame;
                                       NOT reference behaviour, off by default */
+#define SPX_F_EXACT_NORM      0x4u /* NCC without a requested surface normally skips the
+                                      statistics sweep when the standard deviations of
+                                      cc.py:139-154 are provably positive (the shift does
+                                      not depend on a positive scale); this flag forces
+                                      the sweep */
 
 /* ---- per-pair status bits (int32 output) --------------------------------
  * The reference expresses these situations through NaNs and through the

@@ -13,7 +13,7 @@ ABI_VERSION = 1
 E_BADARG, E_UNSUPPORTED, E_WORKSPACE, E_DTYPE = -1, -2, -3, -4
 MAX_CUTOUT, MIN_CUTOUT, MAX_FIT_BOX = 256, 3, 15
 CC, NCC, ZNCC = 0, 1, 2
-F_ZERO_BAD_PHASES, F_ZERO_BAD_REF = 0x1, 0x2
+F_ZERO_BAD_PHASES, F_ZERO_BAD_REF, F_EXACT_NORM = 0x1, 0x2, 0x4
 S_NONFINITE_REF = 0x001
 S_NONFINITE_P00, S_NONFINITE_P10, S_NONFINITE_P01, S_NONFINITE_P11 = 0x2, 0x4, 0x8, 0x10
 S_BAD_NORM, S_PEAK_EDGE, S_NO_MAXIMUM, S_FIT_OUTSIDE = 0x20, 0x40, 0x80, 0x100

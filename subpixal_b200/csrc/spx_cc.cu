@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     __shared__ int s_nrrow;
     if (threadIdx.x == 0) {
         s_nrrow = build_rrow<C>(rrow, rank);
+        for (int k = 0; k < 4; ++k) (&c.xl->det[0][0])[k] = 0u;
     }
     __syncthreads();
     c.n_rrow = s_nrrow;
@@ -318,7 +319,8 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
 
     const size_t icc_elems = size_t(4) * prm.ny * prm.nx;
     const PfMap pfmap = prefetch_map(prm.nx, threadIdx.x & 31);
-    for (int k = unit; k < prm.n; k += nunits) {
+    c.dslot = 0;
+    for (int k = unit; k < prm.n; k += nunits, c.dslot ^= 1) {
         const int p = prm.order ? __ldg(prm.order + k) : k;
         PairJob job;
         job.x1 = 0; job.y1 = 0; job.status0 = 0;
@@ -352,11 +354,11 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
         job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
         if (rank == 0) prefetch_pair<C>(prm, k + nunits, pfmap);
-        // peak == NULL: packed [n,4] float64 result table (dx, dy, peak, status)
-        if (prm.peak)
-            process_pair<C>(c, ex, job, prm.shifts + 2 * size_t(p), prm.peak + p, prm.status + p);
-        else
-            process_pair<C>(c, ex, job, prm.shifts + 4 * size_t(p), nullptr, nullptr);
+        // peak == NULL: packed [n,4] float64 result table (dx, dy, peak, status).  ONE call
+        // site: a second inlined copy of process_pair costs 11 % (instruction cache)
+        const bool packed = prm.peak == nullptr;
+        process_pair<C>(c, ex, job, prm.shifts + (packed ? 4 : 2) * size_t(p),
+                        packed ? nullptr : prm.peak + p, packed ? nullptr : prm.status + p);
     }
     if (C::CL == 2) cg::this_cluster().sync();     // do not exit while the peer may still read my W
 }

@@ -142,6 +142,13 @@ struct Xchg {
     float bestv[2];
     int besti[2];
     int status[2];
+    // degeneracy detector of the statistics-free NCC path (lazy_decide): det[s][0] evidence
+    // bits (1: phases, 2: reference), det[s][1] bits of the largest |pixel| seen; in cluster
+    // mode both CTAs update both copies with atomics.  Two slots, used by alternate pairs:
+    // a CTA clears the NEXT pair's slot between the first and the last cluster barrier of
+    // the current pair - the only window in which the peer can neither still read it
+    // (previous pair) nor already write it (next pair).
+    unsigned det[2][2];
 };
 
 template <class C>
@@ -152,6 +159,7 @@ struct Ctx {
     PairState *ps;
     // cluster mode (CL == 2); rank = 0, col_lo = 0 and null pointers otherwise
     int rank, col_lo, n_rrow;
+    int dslot;             // detector slot of the current pair (alternates, see Xchg)
     cf *Wpeer;             // the peer CTA's W (distributed shared memory)
     Xchg *xl, *xp;         // local / peer exchange block
 };
@@ -203,6 +211,34 @@ template <class C, int K1> SPX_HD cf *w_of_k1(cf *mine, cf *peer, int rank) {
 }
 
 SPX_HD unsigned f32_bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
+SPX_HD float bits_f32(unsigned u) { union { float f; unsigned u; } c; c.u = u; return c.f; }
+// order-preserving map float -> unsigned (so that integer atomicMin / atomicMax order floats)
+SPX_HD unsigned fkey(float v) {
+    const unsigned u = f32_bits(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+SPX_HD float fkey_inv(unsigned k) { return bits_f32((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+SPX_HD void key_min(unsigned *p, unsigned v) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+SPX_HD void key_max(unsigned *p, unsigned v) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+SPX_HD void key_or(unsigned *p, unsigned v) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
 
 // Geometry of one tile column as seen by one lane: pointer to cutout pixel
 // (0, x) and whether that column exists in the source image.  Pixels outside
@@ -358,8 +394,20 @@ SPX_HD void stats_finalize(PairState &ps, const StatPartial &t) {
 // n1 >= NMAX/(2*E2).  No bounds tests, no predicates, minimal address math.
 // CHECK = false: the statistics pass has already scanned these tiles and found
 // them finite, so the NaN/Inf tracking is skipped.
+//
+// lazy (statistics-free NCC path, see lazy_decide): 1 = also track the largest |pixel| of
+// the pass; 2 = and look for evidence that the standard deviations of cc.py:139-154 are
+// positive - two non-zero pixels of image00 / image10 with different values, resp. (in the
+// reference pass, where four rows of image00 ride along as the mask) two reference pixels
+// under the mask "image00 non-zero" with different values.  Two candidate pairs of rows
+// per item are looked at; ANY hit in the CTA is enough.
+SPX_HD bool lazy_evidence(float u, float w) {
+    const float m = fmaxf(fabsf(u), fabsf(w));
+    return fabsf(u - w) >= 1e-3f * m && m >= 1e-12f;
+}
 template <class C, bool FAST, bool IS_REF, bool CHECK = true>
-SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0) {
+SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
+                   int lazy = 0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NXL : local_cols(c, ps.nx), ny = FAST ? C::NMAX : ps.ny;
@@ -371,23 +419,36 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
     constexpr int N1_LO = (FAST && !IS_REF) ? C::NMAX / (2 * C::E2) : 0;
     constexpr int N1_HI = (FAST && IS_REF) ? C::NMAX / C::E2 : C::E1;
     static_assert(!FAST || (C::NMAX / 2) % C::E2 == 0, "fast path needs E2 | NMAX/2");
+    // candidate rows of the evidence search: two pairs around the middle of the rows an
+    // item loads (the middle rows are the ones that exist on the generic path too)
+    constexpr int MID = (N1_LO + N1_HI) / 2;
+    constexpr int A0 = MID - 1, A1 = MID, B0 = (MID + 1 < N1_HI - 2) ? MID + 1 : N1_HI - 2, B1 = B0 + 1;
+    static_assert(A0 >= N1_LO && B1 < N1_HI && B0 >= N1_LO, "evidence rows inside the item");
+    const bool detect = lazy == 2;
     int flags = 0;
+    unsigned amax = 0u;                            // bits of the largest finite |pixel|
+    bool ev = false;
     // an item = (32-column chunk, n2): its loads, and everything after them
     auto load_item = [&](int wi, float (&va)[C::E1], float (&vb)[C::E1]) {
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
         const bool active = FAST || i < nx;
+        // reference pass with `detect`: four rows of image00 ride along in vb as the mask
+        const bool second = pair || detect;
         const TileCol ta = tile_col(ps, sa, c.col_lo + i, active);
-        const TileCol tb = tile_col(ps, pair ? sb : sa, c.col_lo + i, active && pair);
+        const TileCol tb = tile_col(ps, pair ? sb : (detect ? 1 : sa), c.col_lo + i, active && second);
         const int ybase = n2 - yoff;
         const int rs = C::E2 * ta.pitch;                     // elements between loads
         const float *pa0 = ta.p + ybase * ta.pitch;
         const float *pb0 = tb.p + ybase * tb.pitch;
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
+            // generic path: the rows that exist depend on the item, so every row is a candidate
+            constexpr bool cand = !FAST || n1 == A0 || n1 == A1 || n1 == B0 || n1 == B1;
             if constexpr (FAST) {
                 if constexpr (n1 >= N1_LO && n1 < N1_HI) {
                     va[n1] = ld_f32_last(pa0 + n1 * rs);
-                    vb[n1] = pair ? ld_f32_last(pb0 + n1 * rs) : 0.f;
+                    if constexpr (IS_REF) vb[n1] = (cand && detect) ? ld_f32(pb0 + n1 * rs) : 0.f;
+                    else vb[n1] = ld_f32_last(pb0 + n1 * rs);
                 } else {
                     va[n1] = 0.f; vb[n1] = 0.f;
                 }
@@ -395,7 +456,8 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
                 const int y = C::E2 * n1 + ybase;
                 const bool ok = y >= ylo && y < yhi;         // warp-uniform
                 va[n1] = (ok && ta.colok) ? ld_f32_last(pa0 + n1 * rs) : 0.f;
-                vb[n1] = (ok && tb.colok) ? ld_f32_last(pb0 + n1 * rs) : 0.f;
+                if constexpr (IS_REF) vb[n1] = (ok && tb.colok) ? ld_f32(pb0 + n1 * rs) : 0.f;
+                else vb[n1] = (ok && tb.colok) ? ld_f32_last(pb0 + n1 * rs) : 0.f;
             }
         });
     };
@@ -414,11 +476,48 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
             });
         }
         if (CHECK && worst >= 0x7f800000u) {                 // rare
+            worst = 0u;
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
                 va[n1] = sanitize(va[n1], sa, report, flags);
-                vb[n1] = sanitize(vb[n1], pair ? sb : sa, report, flags);
+                if (pair) vb[n1] = sanitize(vb[n1], sb, report, flags);
+                const unsigned ua = f32_bits(va[n1]) & 0x7fffffffu, ub = f32_bits(vb[n1]) & 0x7fffffffu;
+                worst = worst > ua ? worst : ua;
+                if (pair) worst = worst > ub ? worst : ub;
             });
+        }
+        if constexpr (CHECK) amax = amax > worst ? amax : worst;
+        if (!FAST && detect) {
+            // generic path: smallest / largest candidate value of this thread's column
+            float tmin = INFINITY, tmax = -INFINITY;
+            static_for<0, C::E1>([&](auto N1) {
+                constexpr int n1 = decltype(N1)::value;
+                const float a = va[n1], b = vb[n1];
+                if constexpr (IS_REF) {
+                    const bool m = b != 0.f && finitef(b);
+                    tmin = fminf(tmin, m ? a : INFINITY); tmax = fmaxf(tmax, m ? a : -INFINITY);
+                    vb[n1] = 0.f;
+                } else {
+                    const bool za = a != 0.f, zb = b != 0.f;
+                    tmin = fminf(tmin, fminf(za ? a : INFINITY, zb ? b : INFINITY));
+                    tmax = fmaxf(tmax, fmaxf(za ? a : -INFINITY, zb ? b : -INFINITY));
+                }
+            });
+            ev |= tmax >= tmin && lazy_evidence(tmin, tmax);
+        }
+        if (FAST && detect) {
+            if constexpr (IS_REF) {
+                // reference pixels where image00 is non-zero (cc.py:150-154; a non-finite
+                // image00 pixel is either reported or zeroed - not part of the mask)
+                const bool ma = vb[A0] != 0.f && finitef(vb[A0]) && vb[A1] != 0.f && finitef(vb[A1]);
+                const bool mb = vb[B0] != 0.f && finitef(vb[B0]) && vb[B1] != 0.f && finitef(vb[B1]);
+                ev |= (ma && lazy_evidence(va[A0], va[A1])) || (mb && lazy_evidence(va[B0], va[B1]));
+                vb[A0] = 0.f; vb[A1] = 0.f; vb[B0] = 0.f; vb[B1] = 0.f;
+            } else {
+                // non-zero pixels of image00 / image10 (cc.py:134-137)
+                ev |= (va[A0] != 0.f && va[A1] != 0.f && lazy_evidence(va[A0], va[A1])) ||
+                      (vb[B0] != 0.f && vb[B1] != 0.f && lazy_evidence(vb[B0], vb[B1]));
+            }
         }
         cf x[C::E1];
         if (zncc) {
@@ -476,7 +575,50 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0)
             finish_item(wi, va, vb);                         // arithmetic afterwards
         }
     }
+    if (lazy) {
+        unsigned evbit = ev ? (IS_REF ? 2u : 1u) : 0u;
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+        evbit = __reduce_or_sync(0xffffffffu, evbit);
+        amax = __reduce_max_sync(0xffffffffu, amax);
+        if (lane == 0)
+#endif
+        {
+            // det[0]: evidence bits, det[1]: largest |pixel| seen; cluster mode: both copies
+            if (evbit) key_or(&c.xl->det[c.dslot][0], evbit);
+            key_max(&c.xl->det[c.dslot][1], amax);
+            if (C::CL == 2) {
+                if (evbit) key_or(&c.xp->det[c.dslot][0], evbit);
+                key_max(&c.xp->det[c.dslot][1], amax);
+            }
+        }
+    }
     return flags;
+}
+
+// Statistics-free NCC (cc_type NCC, no surface requested).  The pooled sigma and
+// sigma_ref of cc.py:139-154 scale the whole surface by ONE positive number, and the
+// result of the path - argmax, the quadratic-fit position (homogeneous of degree 0 in
+// the samples) and every sign test of centroid.py:216-236 - does not depend on a
+// positive scale.  The statistics only decide the degenerate cases (no non-zero pixel
+// -> std of an empty set -> NaN surface; sigma or sigma_ref == 0 -> division by zero),
+// so it is enough to PROVE both deviations positive.  Evidence: two pixels of the set a
+// deviation is taken over (non-zero pixels of the four phases; reference pixels under
+// the union mask) whose values differ by >= 1e-3 of the larger magnitude.  If the value
+// M of largest magnitude in the set and a value v0 with |v0 - M| >= ~1e-3 |M| both
+// exist - which two such pixels imply - then var >= (1e-3 M)^2 / (2 n) while the mean
+// square is <= M^2, a ratio >= 5e-7 / n that the float64 sums of the exact path
+// (relative error ~ 1e-16) cannot cancel for any n up to 4 * 256^2.  With every |pixel| in
+// [0, 1e12] (and the evidence pixels >= 1e-12) neither the unnormalised surface nor the
+// exact path's scale leaves the float32 range.  Anything else - all-zero or constant
+// tiles, a single unmasked pixel, extreme magnitudes - falls back to the exact path.
+SPX_HD bool lazy_decide(const unsigned (&det)[2], bool need_evidence) {
+#ifdef SPX_LAZY_NODETECT
+    need_evidence = false;
+#endif
+#ifdef SPX_LAZY_NOREF
+    return (!need_evidence || (det[0] & 1u) == 1u) && det[1] <= 0x5368d4a5u;
+#endif
+    return (!need_evidence || (det[0] & 3u) == 3u) && det[1] <= 0x5368d4a5u /* 1e12f */;
 }
 
 // C2: E2-point FFT over n2 for every (column, k1 group of mine), in place.
@@ -903,8 +1045,15 @@ SPX_HD void fill_state(PairState &ps, const PairJob &job, int part) {
 // --------------------------------------------------------------------------
 // reference transform + the two phase pairs (see the data flow at the top)
 // --------------------------------------------------------------------------
+// lazy: statistics-free NCC attempt; returns false (after a C1 pass over image tiles) when
+// the detector could not prove the normalisation well defined.
+#ifdef SPX_LAZY_NODETECT                 // developer knob: cost of the detector (results unchecked)
+constexpr int kLazyDetect = 0;
+#else
+constexpr int kLazyDetect = 2;
+#endif
 template <class C, bool FAST, bool CHECK, class Ex>
-SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
+SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
     PairState *ps = c.ps;
     // placement offset of the image tiles and the resulting index shift of the
     // wanted lags: sample m of the circular correlation is lag (m - off)
@@ -916,7 +1065,11 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 
     // ---- reference image -> conj(R) * scale, half spectrum ---------------
     ex.par([&](int tid) {
-        const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0);
+#ifdef SPX_LAZY_NOREF                    // developer knob: cost of the reference-side detector
+        const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0, lazy ? 1 : 0);
+#else
+        const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0, lazy ? kLazyDetect : 0);
+#endif
         if (fl) ex.or_status(&ps->status, fl);
     });
     if (C::CL == 2) ex.cluster_sync();           // the peer's half of my rows has arrived
@@ -935,11 +1088,15 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
+        const int lz = lazy ? (b == 0 ? kLazyDetect : 1) : 0;
         ex.par([&](int tid) {
-            const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin);
+            const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin, lz);
             if (fl) ex.or_status(&ps->status, fl);
         });
         if (C::CL == 2) ex.cluster_sync();       // the peer's half of my rows has arrived
+        // (the detector keys of both CTAs are complete after this barrier; every thread
+        // evaluates the same few comparisons, so the branch is uniform)
+        if (lazy && !lazy_decide(c.xl->det[c.dslot], b == 0)) return false;
         ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
         if (C::INPLACE) {
             ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
@@ -961,6 +1118,7 @@ SPX_HD void run_transforms(Ctx<C> &c, Ex &ex) {
         // them; after the second pair the exchange barrier of the peak stage does that
         if (C::CL == 2 && b == 0) ex.cluster_sync();
     }
+    return true;
 }
 
 // --------------------------------------------------------------------------
@@ -982,49 +1140,71 @@ template <class C, class Ex>
 SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
                          double *shift2, int *peak, int *status) {
     PairState *ps = c.ps;
-    ex.parts(6, [&](int part) { fill_state(*ps, job, part); });
-
-    // ---- normalisation statistics (cc.py:131-156) ----------------------
-    if (job.cc_type != SPX_CC) {
-        StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(c, tid); });
-        if (C::CL == 2) {
-            // each CTA scanned its half of the columns: exchange and add in a fixed
-            // order so that both CTAs derive bit-identical statistics
-            ex.single([&]() {
-                const double v[8] = {tot.cnt, tot.sum, tot.sq, tot.rcnt, tot.rsum, tot.rsq,
-                                     double(tot.flags), 0.0};
-                for (int k = 0; k < 8; ++k) { c.xl->stat[c.rank][k] = v[k]; c.xp->stat[c.rank][k] = v[k]; }
-            });
-            ex.cluster_sync();
-            ex.single([&]() {
-                StatPartial t = stat_zero();
-                for (int rk = 0; rk < 2; ++rk) {
-                    const double *v = c.xl->stat[rk];
-                    t.cnt += v[0]; t.sum += v[1]; t.sq += v[2];
-                    t.rcnt += v[3]; t.rsum += v[4]; t.rsq += v[5]; t.flags |= int(v[6]);
-                }
-                stats_finalize(*ps, t);
-            });
-        } else {
-            ex.single([&]() { stats_finalize(*ps, tot); });
-        }
-    }
-
     const bool fast = job.ny == C::NMAX && job.nx == C::NMAX && job.x1 >= 0 && job.y1 >= 0 &&
                       job.x1 + job.nx <= job.W && job.y1 + job.ny <= job.H;
-    // tiles already scanned by the statistics pass and found finite -> no NaN tracking
     const int nonfinite = SPX_S_NONFINITE_REF | SPX_S_NONFINITE_P00 | SPX_S_NONFINITE_P10 |
                           SPX_S_NONFINITE_P01 | SPX_S_NONFINITE_P11;
-    const bool check = job.cc_type == SPX_CC || (ps->status & (nonfinite | kSawNonFinite)) != 0;
-    if constexpr (C::HAS_FAST) {
-        if (fast) {
-            if (check) run_transforms<C, true, true>(c, ex);
-            else run_transforms<C, true, false>(c, ex);
-        } else {
-            run_transforms<C, false, true>(c, ex);
+    // NCC without a requested surface: first try without the statistics sweep (lazy_decide).
+    // ONE loop body serves both attempts: a second inlined copy of the transforms would
+    // not fit the instruction cache.
+    bool lazy = job.cc_type == SPX_NCC && !job.patch_icc && !(job.flags & SPX_F_EXACT_NORM);
+#ifdef SPX_NO_LAZY                       // developer knob (tools/variant.sh): A/B of the sweep
+    lazy = false;
+#endif
+#if !defined(SPX_HOST_EMU)
+#pragma unroll 1
+#endif
+    for (;;) {
+        ex.parts(7, [&](int part) {
+            if (part < 6) { fill_state(*ps, job, part); return; }
+            // single CTA: nobody else touches the detector slot (cluster mode: see Xchg)
+            if (C::CL == 1) { c.xl->det[c.dslot][0] = 0u; c.xl->det[c.dslot][1] = 0u; }
+        });
+
+        // ---- normalisation statistics (cc.py:131-156) ----------------------
+        if (job.cc_type != SPX_CC && !lazy) {
+            StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(c, tid); });
+            if (C::CL == 2) {
+                // each CTA scanned its half of the columns: exchange and add in a fixed
+                // order so that both CTAs derive bit-identical statistics
+                ex.single([&]() {
+                    const double v[8] = {tot.cnt, tot.sum, tot.sq, tot.rcnt, tot.rsum, tot.rsq,
+                                         double(tot.flags), 0.0};
+                    for (int k = 0; k < 8; ++k) { c.xl->stat[c.rank][k] = v[k]; c.xp->stat[c.rank][k] = v[k]; }
+                });
+                ex.cluster_sync();
+                ex.single([&]() {
+                    StatPartial t = stat_zero();
+                    for (int rk = 0; rk < 2; ++rk) {
+                        const double *v = c.xl->stat[rk];
+                        t.cnt += v[0]; t.sum += v[1]; t.sq += v[2];
+                        t.rcnt += v[3]; t.rsum += v[4]; t.rsq += v[5]; t.flags |= int(v[6]);
+                    }
+                    stats_finalize(*ps, t);
+                });
+            } else {
+                ex.single([&]() { stats_finalize(*ps, tot); });
+            }
         }
-    } else {
-        run_transforms<C, false, true>(c, ex);
+
+        // tiles already scanned by the statistics pass and found finite -> no NaN tracking
+        const bool check = lazy || job.cc_type == SPX_CC ||
+                           (ps->status & (nonfinite | kSawNonFinite)) != 0;
+        bool done;
+        if constexpr (C::HAS_FAST) {
+            if (fast) {
+                if (check) done = run_transforms<C, true, true>(c, ex, lazy);
+                else done = run_transforms<C, true, false>(c, ex, false);
+            } else {
+                done = run_transforms<C, false, true>(c, ex, lazy);
+            }
+        } else {
+            done = run_transforms<C, false, true>(c, ex, lazy);
+        }
+        if (done) break;
+        lazy = false;                   // degenerate or extreme input: the exact path decides
+        // in cluster mode the peer may still be inside its detector pass; nothing it
+        // writes from now on (its own W rows) is touched before the next cluster barrier
     }
 
     // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
@@ -1034,6 +1214,7 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
             c.xl->bestv[c.rank] = ps->best.v; c.xp->bestv[c.rank] = ps->best.v;
             c.xl->besti[c.rank] = ps->best.idx; c.xp->besti[c.rank] = ps->best.idx;
             c.xl->status[c.rank] = ps->status; c.xp->status[c.rank] = ps->status;
+            c.xl->det[c.dslot ^ 1][0] = 0u; c.xl->det[c.dslot ^ 1][1] = 0u;   // next pair's slot
         });
         // the cluster barrier is a release/acquire fence at cluster scope: my part of
         // the surface (global memory) is visible to rank 0 after it

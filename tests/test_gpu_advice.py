@@ -34,8 +34,13 @@ def test_big_endian_and_integer_frames():
         got = cutout.Cutout(ints, None, blc=(-3, 2), trc=(20, 30), mode="fill", fillval=7)
         assert got.data.dtype == dt and np.array_equal(got.data, want["data"])
         assert np.array_equal(got.mask, want["mask"])
-    with pytest.raises(ValueError):                          # np.full(..., nan, dtype=int)
-        cutout.Cutout(ints, None, blc=(-3, 2), trc=(20, 30), mode="fill")
+    # the default fillval (NaN) in an integer frame is whatever np.full makes of it
+    # (cutout.py:737; a RuntimeWarning and INT_MIN with numpy 2.x) - same call here
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = orc.crop(ints, (-3, 2), (20, 30), mode="fill")
+        got = cutout.Cutout(ints, None, blc=(-3, 2), trc=(20, 30), mode="fill")
+    assert np.array_equal(got.data, want["data"])
     # find_peak on a big-endian surface
     surf = rng.standard_normal((20, 20))
     surf[7, 9] += 10
@@ -99,9 +104,11 @@ def test_frame_displacements_dq_and_oversize():
     ib2 = np.concatenate([ib[:5], [[0, 0, 299, 40]], ib[5:]])
     db2 = np.concatenate([db[:5], [[0, 0, 305, 45]], db[5:]])
     e = align.frame_displacements(t(img), t(drz), ib2, db2, fmap, full_output=True)
-    keep = [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12]
-    assert torch.equal(e[0][keep], d[0]) and torch.equal(e[1][keep], d[1])
-    assert bool(torch.isnan(e[0][5]).all()) and int(e[1][5]) == -1 and int(e[2][5]) == L.S_UNSUPPORTED_SIZE
     f = align.frame_displacements(t(img), t(drz), ib, db, fmap, full_output=True)
+    keep = [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12]
+    assert torch.equal(e[0][keep], f[0]) and torch.equal(e[1][keep], f[1])
+    assert bool(torch.isnan(e[0][5]).all()) and int(e[1][5]) == -1 and int(e[2][5]) == L.S_UNSUPPORTED_SIZE
+    e2 = align.frame_displacements(t(img), t(drz), ib2, db2, fmap)          # no surfaces
+    assert torch.equal(e2[0][keep], d[0]) and bool(torch.isnan(e2[0][5]).all())
     assert torch.equal(e[3][:int(e[4][5])], f[3][:int(f[4][5])])
     assert bool(torch.isnan(e[3][int(e[4][5]):int(e[4][6])]).all())

@@ -3,7 +3,8 @@
 // index arithmetic can be debugged in a container without a GPU.
 //   g++ -std=c++17 -DSPX_HOST_EMU -O2 -x c++ -o /tmp/host_emu tools/host_emu.cu
 //   /tmp/host_emu in.bin out.bin
-// in.bin : int32 n, ny, nx, cc_type, want_frames(0) ; float32 [n,5,ny,nx]
+// in.bin : int32 n, ny, nx, cc_type, no_icc (1: surface not requested -> the
+//          statistics-free NCC path may run) ; float32 [n,5,ny,nx]
 // out.bin: float64 [n,2] shifts ; int32 [n] peak ; int32 [n] status ; float32 [n,2ny,2nx]
 #include <pthread.h>
 #include <cstdio>
@@ -49,6 +50,8 @@ struct HostExec {
     float load_icc(const float *p) { return *p; }
 };
 
+static bool g_no_icc = false;
+
 template <class C>
 void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts, int *peak,
          int *status, float *icc) {
@@ -68,6 +71,7 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
         c[rk].n_rrow = build_rrow<C>(rrow[rk].data(), rk);
         c[rk].rank = rk; c[rk].col_lo = rk * C::NXL;
         c[rk].xl = &xc[rk];
+        for (int k = 0; k < 4; ++k) (&xc[rk].det[0][0])[k] = 0u;
     }
     for (int rk = 0; rk < CL; ++rk) {
         c[rk].Wpeer = CL == 2 ? W[rk ^ 1].data() : nullptr;
@@ -78,12 +82,13 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
         HostExec<C> ex;
         ex.bar = &bar;
         for (int p = 0; p < n; ++p) {
+            c[rk].dslot = p & 1;
             c[rk].icc = icc + size_t(p) * 4 * tile;
             PairJob job;
             for (int s = 0; s < 5; ++s) job.base[s] = stack + (size_t(p) * 5 + s) * tile;
             job.pitch = nx; job.H = ny; job.W = nx; job.x1 = 0; job.y1 = 0;
             job.ny = ny; job.nx = nx; job.cc_type = cc_type; job.status0 = 0;
-            job.flags = 0; job.patch_icc = true;
+            job.flags = 0; job.patch_icc = !g_no_icc;
             process_pair<C>(c[rk], ex, job, shifts + 2 * p, peak + p, status + p);
         }
     };
@@ -103,6 +108,7 @@ int main(int argc, char **argv) {
     int hdr[5];
     if (!f || fread(hdr, 4, 5, f) != 5) return 3;
     const int n = hdr[0], ny = hdr[1], nx = hdr[2], cc_type = hdr[3];
+    g_no_icc = hdr[4] != 0;
     std::vector<float> stack(size_t(n) * 5 * ny * nx);
     if (fread(stack.data(), 4, stack.size(), f) != stack.size()) return 4;
     fclose(f);

@@ -76,7 +76,25 @@ struct CcParams {
 using Cfg20  = CcCfg< 32,  4,  8,  20, SPX20_T, SPX20_MINB, true,  true,  true>;
 using Cfg42  = CcCfg< 64,  8,  8,  42, SPX42_T, SPX42_MINB, true,  true,  true>;
 using Cfg84  = CcCfg<128,  8, 16,  84, SPX84_T, 1, true,  true,  true>;
+// 170 / 256 px classes: W and R either in a per-CTA global slab (default) or in the shared
+// memory of a 4- / 8-CTA cluster (row split of W and R like the 128 px class, mirrored R
+// rows over DSMEM).  The cluster forms move exactly the algorithmic bytes through DRAM
+// (1.0x instead of 14.5x at 256 px) but spend a third of their time in the 9 cluster-wide
+// barriers per pair (the slowest of 8 CTAs sets the pace of every pass): 139 k vs 177 k
+// pairs/s at 256 px, 354 k vs 391 k at 170 px (profiles/r2_cc_fit_cfg256_cluster8_*), so
+// the slab forms stay the default; -DSPX256_CLUSTER=1 / -DSPX170_CLUSTER=1 select the
+// cluster forms (parity-tested on the GPU and by tests/test_emulator.py).
+#ifndef SPX170_CLUSTER
+#define SPX170_CLUSTER 0
+#endif
+#ifndef SPX170_T
+#define SPX170_T 512
+#endif
+#if SPX170_CLUSTER
+using Cfg170 = CcCfg<256, 16, 16, 170, SPX170_T, 1, true, true, true, 4>;  // 4-CTA cluster, DSMEM
+#else
 using Cfg170 = CcCfg<256, 16, 16, 170, 512, 1, false, false>;              // W / R in a global slab
+#endif
 using Cfg32  = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32_MINB, true,  true,  true>;
 using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, true,  true,  true>;
 #ifndef SPX128_CLUSTER
@@ -93,10 +111,23 @@ using Cfg128 = CcCfg<192, 12, 16, 128, SPX128_T, 1, true,  true,  SPX128_INPLACE
 #else
 using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
 #endif
+#ifndef SPX256_CLUSTER
+#define SPX256_CLUSTER 0
+#endif
+#if SPX256_CLUSTER
+#ifndef SPX256_T
+#define SPX256_T 384
+#endif
+using Cfg256 = CcCfg<384, 24, 16, 256, SPX256_T, 1, true, true, true, 8>;  // 8-CTA cluster, DSMEM
+#else
 #ifndef SPX256_T
 #define SPX256_T 512
 #endif
-using Cfg256 = CcCfg<384, 24, 16, 256, SPX256_T, 1, false, false>;
+#ifndef SPX256_MINB
+#define SPX256_MINB 1
+#endif
+using Cfg256 = CcCfg<384, 24, 16, 256, SPX256_T, SPX256_MINB, false, false>;   // W / R in a global slab
+#endif
 
 template <class C> struct Layout {
     // shared memory carve-up (bytes); everything 16-byte aligned
@@ -104,7 +135,7 @@ template <class C> struct Layout {
     static constexpr size_t off_red = 256;                       // reductions
     static constexpr size_t red_bytes = 32 * 8 * 8;              // [32 warps][8] doubles
     static constexpr size_t off_xchg = off_red + red_bytes;       // Xchg (cluster mode)
-    static constexpr size_t off_rrow = off_xchg + 256;
+    static constexpr size_t off_rrow = off_xchg + 640;
     static constexpr size_t rrow_bytes = ((C::RH * 2 + 15) / 16) * 16;
     static constexpr size_t off_xrow = off_rrow + rrow_bytes;
     static constexpr size_t xrow_bytes = 0;
@@ -113,7 +144,7 @@ template <class C> struct Layout {
     static constexpr size_t off_R = off_W + (C::W_SMEM ? C::W_ELEMS * 8 : 0);
     static constexpr size_t total = off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0);
     static_assert(sizeof(PairState) <= 256, "PairState must fit its slot");
-    static_assert(sizeof(Xchg) <= 256, "Xchg must fit its slot");
+    static_assert(sizeof(Xchg) <= 640, "Xchg must fit its slot");
 };
 
 __device__ __forceinline__ Best warp_best(Best b) {
@@ -283,7 +314,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     using L = Layout<C>;
     uint16_t *rrow = reinterpret_cast<uint16_t *>(smem + L::off_rrow);
     // one pair per CTA, or per cluster of CL CTAs
-    const int rank = C::CL == 2 ? int(cg::this_cluster().block_rank()) : 0;
+    const int rank = C::CL > 1 ? int(cg::this_cluster().block_rank()) : 0;
     const int unit = blockIdx.x / C::CL, nunits = gridDim.x / C::CL;
     unsigned char *slab = prm.workspace + size_t(unit) * prm.slab_bytes;
 
@@ -298,12 +329,6 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     c.rank = rank;
     c.col_lo = rank * C::NXL;
     c.xl = reinterpret_cast<Xchg *>(smem + L::off_xchg);
-    c.Wpeer = nullptr; c.xp = nullptr;
-    if (C::CL == 2) {
-        cg::cluster_group cluster = cg::this_cluster();
-        c.Wpeer = cluster.map_shared_rank(c.W, rank ^ 1);
-        c.xp = cluster.map_shared_rank(c.xl, rank ^ 1);
-    }
 
     DevExec<C> ex;
     ex.red = reinterpret_cast<double *>(smem + L::off_red);
@@ -315,7 +340,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     }
     __syncthreads();
     c.n_rrow = s_nrrow;
-    if (C::CL == 2) cg::this_cluster().sync();     // the peer is resident: DSMEM may be used
+    if (C::CL > 1) cg::this_cluster().sync();      // the peers are resident: DSMEM may be used
 
     const size_t icc_elems = size_t(4) * prm.ny * prm.nx;
     const PfMap pfmap = prefetch_map(prm.nx, threadIdx.x & 31);
@@ -360,7 +385,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
         process_pair<C>(c, ex, job, prm.shifts + (packed ? 4 : 2) * size_t(p),
                         packed ? nullptr : prm.peak + p, packed ? nullptr : prm.status + p);
     }
-    if (C::CL == 2) cg::this_cluster().sync();     // do not exit while the peer may still read my W
+    if (C::CL > 1) cg::this_cluster().sync();      // do not exit while a peer may still read my W / R
 }
 
 // ---- host side ------------------------------------------------------------------
@@ -449,7 +474,7 @@ static int launch(CcParams &prm, const SlabPlan &sp, cudaStream_t stream) {
             if (max_clusters[dev] == 0) {
                 int mc = 0;
                 cudaLaunchConfig_t q = cfg;
-                q.gridDim = dim3(num_sms() * C::MINB);
+                q.gridDim = dim3(num_sms() * C::MINB / C::CL * C::CL);      // whole clusters
                 if (cudaOccupancyMaxActiveClusters(&mc, cc_fit_kernel<C>, &q) != cudaSuccess || mc <= 0) {
                     cudaGetLastError();
                     mc = -1;

@@ -27,6 +27,9 @@
 // ky in [0, P/2], Hermitian symmetry supplies the rest).
 #pragma once
 #include <limits.h>
+#if !defined(SPX_HOST_EMU)
+#include <cooperative_groups.h>
+#endif
 #include "spx_common.cuh"
 #include "spx_fft.cuh"
 #include "spx_peak.cuh"
@@ -74,14 +77,17 @@ template <class C, bool INV = false> SPX_HD cf tw2(int n2, int k1) {
 // P x (NMAX+1) and the row stage goes through a 32-row scratch S, batch by batch
 // (used when W lives in global memory).
 //
-// CL = 2: one pair is processed by a thread-block cluster of two CTAs.  W is
+// CL = 2, 4, 8: one pair is processed by a thread-block cluster of CL CTAs.  W is
 // split by ROWS: the rows r = k1*E2 + k2 of one k1 group all have ky = k1 + E1*k2
-// of the same parity as k1 (E1 even), hence the same parity of q = min(ky, P-ky).
-// CTA `rank` owns the groups with k1 % 2 == rank: C2, the whole row stage and IC1
-// are then purely local and need only the R rows of parity `rank` (half of R).
-// Only C1 (stores half of its outputs into the peer's shared memory) and IC2
-// (loads half of its inputs from it) cross the cluster, through DSMEM; the tile
-// columns, and therefore all HBM traffic, are split half / half.
+// congruent to k1 modulo CL (CL divides E1).  CTA `rank` owns the groups with
+// k1 % CL == rank: C2, the whole row stage and IC1 are then purely local.  The half
+// spectrum R is split the same way - row q lives in CTA q % CL at local row q / CL:
+// a W row with ky <= P/2 finds its R row (q = ky) at home, a row with ky > P/2 needs
+// q = P - ky, which is congruent to -rank: the rows of CTA (CL - rank) % CL, read over
+// DSMEM (for CL = 2 that is the CTA itself).  Besides those reads only C1 (it stores the
+// outputs of the k1 groups it does not own into their owners' shared memory) and IC2
+// (it loads them back) cross the cluster; the tile columns, and therefore all HBM
+// traffic, are split evenly.
 template <int P_, int E1_, int E2_, int NMAX_, int T_, int MINB_, bool WSM_, bool RSM_,
           bool INPLACE_ = false, int CL_ = 1>
 struct CcCfg {
@@ -90,9 +96,9 @@ struct CcCfg {
     static constexpr int CL = CL_;
     // the compile-time fast path for full-size interior cutouts places the tiles at
     // offset NMAX/2, which must be a multiple of E2 (see c1_pass)
-    static constexpr bool HAS_FAST = (NMAX_ / 2) % E2_ == 0;
+    static constexpr bool HAS_FAST = (NMAX_ / 2) % E2_ == 0 && NMAX_ % CL_ == 0;
     static constexpr int NW = T / 32;
-    static constexpr int NXL = NMAX / CL;    // tile columns loaded / finished by one CTA
+    static constexpr int NXL = (NMAX + CL - 1) / CL;   // tile columns loaded / finished by one CTA
     static constexpr int E1L = E1 / CL;      // k1 groups (of E2 rows each) held by one CTA
     static constexpr int PL = P / CL;        // rows of W held by one CTA
     static constexpr int WP = INPLACE ? P + 1 : NMAX + 1;   // pitch of W (complex), odd
@@ -108,8 +114,10 @@ struct CcCfg {
     static constexpr size_t W_ELEMS = size_t(PL) * WP;
     static constexpr size_t S_ELEMS = INPLACE ? 0 : size_t(BATCH) * SP;
     static constexpr size_t R_ELEMS = size_t(RHL) * RP;
-    static_assert(CL == 1 || (CL == 2 && WSM_ && RSM_ && E1 % 2 == 0),
-                  "cluster mode: W and R in shared memory, even E1");
+    static_assert(CL == 1 || ((CL == 2 || CL == 4 || CL == 8) && WSM_ && RSM_ && INPLACE_ &&
+                              E1 % CL == 0 && P % CL == 0),
+                  "cluster mode: W and R in shared memory, CL divides E1 and P");
+
     static_assert(E1 * E2 == P, "P = E1*E2");
     static_assert(P % 2 == 0 && NMAX % 2 == 0, "even sizes");
     static_assert(T % 32 == 0, "whole warps");
@@ -135,13 +143,14 @@ struct PairState {
     Best best;             // running argmax over the interlaced surface
 };
 
-// Values the two CTAs of a cluster hand to each other (each CTA writes slot
-// [rank] of BOTH copies, then a cluster barrier, then reads its local copy).
+// Values the CTAs of a cluster hand to each other (each CTA writes slot [rank] of
+// EVERY copy, then a cluster barrier, then reads its local copy).
+constexpr int kMaxCluster = 8;
 struct Xchg {
-    double stat[2][8];
-    float bestv[2];
-    int besti[2];
-    int status[2];
+    double stat[kMaxCluster][8];
+    float bestv[kMaxCluster];
+    int besti[kMaxCluster];
+    int status[kMaxCluster];
     // degeneracy detector of the statistics-free NCC path (lazy_decide): det[s][0] evidence
     // bits (1: phases, 2: reference), det[s][1] bits of the largest |pixel| seen; in cluster
     // mode both CTAs update both copies with atomics.  Two slots, used by alternate pairs:
@@ -157,12 +166,57 @@ struct Ctx {
     float *icc;            // [2ny][2nx] interlaced surface of this pair
     const uint16_t *rrow;  // my rows of W (local index) with ky <= P/2
     PairState *ps;
-    // cluster mode (CL == 2); rank = 0, col_lo = 0 and null pointers otherwise
+    // cluster mode (CL > 1); rank = 0 and col_lo = 0 otherwise
     int rank, col_lo, n_rrow;
     int dslot;             // detector slot of the current pair (alternates, see Xchg)
-    cf *Wpeer;             // the peer CTA's W (distributed shared memory)
-    Xchg *xl, *xp;         // local / peer exchange block
+    Xchg *xl;              // local exchange block
+#ifdef SPX_HOST_EMU        // the emulator keeps a table of every CTA's buffers
+    cf *Wall[kMaxCluster], *Rall[kMaxCluster];
+    Xchg *xall[kMaxCluster];
+#endif
 };
+
+// The same shared-memory object in CTA `r` of the cluster (distributed shared memory).
+template <class C, class T> SPX_HD T *dsmem_peer(T *local, int r) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    if (C::CL == 1) return local;
+    return cooperative_groups::this_cluster().map_shared_rank(local, r);
+#else
+    (void)r;
+    return local;
+#endif
+}
+template <class C> SPX_HD cf *W_of(const Ctx<C> &c, int r) {
+#ifdef SPX_HOST_EMU
+    return C::CL == 1 ? c.W : c.Wall[r];
+#else
+    return dsmem_peer<C>(c.W, r);
+#endif
+}
+template <class C> SPX_HD cf *R_of(const Ctx<C> &c, int r) {
+#ifdef SPX_HOST_EMU
+    return C::CL == 1 ? c.R : c.Rall[r];
+#else
+    return dsmem_peer<C>(c.R, r);
+#endif
+}
+template <class C> SPX_HD Xchg *X_of(const Ctx<C> &c, int r) {
+#ifdef SPX_HOST_EMU
+    return C::CL == 1 ? c.xl : c.xall[r];
+#else
+    return dsmem_peer<C>(c.xl, r);
+#endif
+}
+// W base pointers of all CTAs of the cluster, indexed by compile-time k1 % CL
+template <class C> struct WBases { cf *p[C::CL]; };
+template <class C> SPX_HD WBases<C> w_bases(const Ctx<C> &c) {
+    WBases<C> b;
+    static_for<0, C::CL>([&](auto Rk) {
+        constexpr int r = decltype(Rk)::value;
+        b.p[r] = W_of<C>(c, r);
+    });
+    return b;
+}
 
 // number of tile columns held by this CTA
 template <class C>
@@ -205,10 +259,7 @@ SPX_HD float ld_f32_last(const float *p) {
 template <class C> SPX_HD int ky_of_row(int lr, int rank) {
     return (lr / C::E2) * C::CL + rank + C::E1 * (lr % C::E2);
 }
-// base pointer and local row of W row (k1, k2) as seen from CTA `c.rank`
-template <class C, int K1> SPX_HD cf *w_of_k1(cf *mine, cf *peer, int rank) {
-    return (C::CL == 1 || (K1 % C::CL) == rank) ? mine : peer;
-}
+
 
 SPX_HD unsigned f32_bits(float v) { union { float f; unsigned u; } c; c.f = v; return c.u; }
 SPX_HD float bits_f32(unsigned u) { union { float f; unsigned u; } c; c.u = u; return c.f; }
@@ -292,7 +343,7 @@ SPX_HD StatPartial stats_thread(const Ctx<C> &c, int tid) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int report = ps.report, ylo = ps.ylo, yhi = ps.yhi;
     int xlo = ps.xlo, xhi = ps.xhi;
-    if (C::CL == 2) {                       // my half of the columns
+    if (C::CL > 1) {                        // my share of the columns
         if (xlo < c.col_lo) xlo = c.col_lo;
         if (xhi > c.col_lo + C::NXL) xhi = c.col_lo + C::NXL;
     }
@@ -425,6 +476,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
     constexpr int A0 = MID - 1, A1 = MID, B0 = (MID + 1 < N1_HI - 2) ? MID + 1 : N1_HI - 2, B1 = B0 + 1;
     static_assert(A0 >= N1_LO && B1 < N1_HI && B0 >= N1_LO, "evidence rows inside the item");
     const bool detect = lazy == 2;
+    const WBases<C> wr = w_bases<C>(c);
     int flags = 0;
     unsigned amax = 0u;                            // bits of the largest finite |pixel|
     bool ev = false;
@@ -543,7 +595,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
             const int gi = c.col_lo + i + col0;              // column inside W
             static_for<0, C::E1>([&](auto K1) {
                 constexpr int k1 = decltype(K1)::value;
-                cf *wb = w_of_k1<C, k1>(c.W, c.Wpeer, c.rank);   // owner of the k1 group
+                cf *wb = wr.p[k1 % C::CL];                       // owner of the k1 group
                 wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gi] = cmul(x[k1], tw2<C>(n2, k1));
             });
         }
@@ -584,11 +636,10 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
 #endif
         {
             // det[0]: evidence bits, det[1]: largest |pixel| seen; cluster mode: both copies
-            if (evbit) key_or(&c.xl->det[c.dslot][0], evbit);
-            key_max(&c.xl->det[c.dslot][1], amax);
-            if (C::CL == 2) {
-                if (evbit) key_or(&c.xp->det[c.dslot][0], evbit);
-                key_max(&c.xp->det[c.dslot][1], amax);
+            for (int r = 0; r < C::CL; ++r) {
+                Xchg *x = X_of<C>(c, r);
+                if (evbit) key_or(&x->det[c.dslot][0], evbit);
+                key_max(&x->det[c.dslot][1], amax);
             }
         }
     }
@@ -681,6 +732,7 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
     const int w2 = 2 * ps.nx;
     float *icc = c.icc;
     const int cbase = 2 * c.col_lo;              // my columns start at surface column 2*col_lo
+    const WBases<C> wr = w_bases<C>(c);
     Best best = best_init();
     SPX_UNROLL_BIG
     for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
@@ -690,7 +742,7 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
         const int gl = c.col_lo + l + col0;                 // column inside W
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
-            const cf *wb = w_of_k1<C, k1>(c.W, c.Wpeer, c.rank);
+            const cf *wb = wr.p[k1 % C::CL];
             x[k1] = wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gl];
         });
         RegFFT<C::E1, true>::run(x);
@@ -833,6 +885,7 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int cb, int ce) {
 template <class C>
 SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
     const int warp = warp_of(tid), lane = tid & 31;
+    const cf *Rmir = R_of<C>(c, (C::CL - c.rank) % C::CL);
     SPX_UNROLL_SMALL
     for (int wi = cb * C::E1 + warp; wi < ce * C::E1; wi += C::NW) {
         const int chunk = wi / C::E1, k1 = wi - chunk * C::E1;
@@ -841,7 +894,8 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         cf *srow = srow_of<C>(c, r, lane);
         const int ky = r >= 0 ? ky_of_row<C>(r, c.rank) : 0;
         const bool flip = ky > C::P / 2;
-        const cf *Rrow = c.R + rmap<C>(flip ? C::P - ky : ky) * C::RP;
+        // the mirrored row P - ky belongs to CTA (CL - rank) % CL (see CcCfg)
+        const cf *Rrow = (flip ? Rmir : c.R) + rmap<C>(flip ? C::P - ky : ky) * C::RP;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
@@ -1072,7 +1126,7 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
 #endif
         if (fl) ex.or_status(&ps->status, fl);
     });
-    if (C::CL == 2) ex.cluster_sync();           // the peer's half of my rows has arrived
+    if (C::CL > 1) ex.cluster_sync();           // the peer's half of my rows has arrived
     ex.par([&](int tid) { c2_pass<C>(c, tid, 0); });
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, 0, C::RCHUNK, 0); });
@@ -1084,7 +1138,7 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
             ex.par([&](int tid) { x2_ref_pass<C>(c, tid, b, b + 1); });
         }
     }
-    if (C::CL == 2) ex.cluster_sync();           // I am done with W: the peer's next C1 may write it
+    if (C::CL > 1) ex.cluster_sync();           // I am done with W: the peer's next C1 may write it
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
     for (int b = 0; b < 2; ++b) {
@@ -1093,7 +1147,7 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
             const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin, lz);
             if (fl) ex.or_status(&ps->status, fl);
         });
-        if (C::CL == 2) ex.cluster_sync();       // the peer's half of my rows has arrived
+        if (C::CL > 1) ex.cluster_sync();       // the peer's half of my rows has arrived
         // (the detector keys of both CTAs are complete after this barrier; every thread
         // evaluates the same few comparisons, so the branch is uniform)
         if (lazy && !lazy_decide(c.xl->det[c.dslot], b == 0)) return false;
@@ -1112,11 +1166,11 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
             }
         }
         ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });
-        if (C::CL == 2) ex.cluster_sync();       // the peer's rows hold their lags: IC2 may read them
+        if (C::CL > 1) ex.cluster_sync();       // the peer's rows hold their lags: IC2 may read them
         ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh, cout); });
         // the peer must not start writing my rows (its next C1) while I still read
         // them; after the second pair the exchange barrier of the peak stage does that
-        if (C::CL == 2 && b == 0) ex.cluster_sync();
+        if (C::CL > 1 && b == 0) ex.cluster_sync();
     }
     return true;
 }
@@ -1164,18 +1218,21 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
         // ---- normalisation statistics (cc.py:131-156) ----------------------
         if (job.cc_type != SPX_CC && !lazy) {
             StatPartial tot = ex.reduce_stats([&](int tid) { return stats_thread<C>(c, tid); });
-            if (C::CL == 2) {
-                // each CTA scanned its half of the columns: exchange and add in a fixed
-                // order so that both CTAs derive bit-identical statistics
+            if (C::CL > 1) {
+                // each CTA scanned its share of the columns: exchange and add in a fixed
+                // order so that all CTAs derive bit-identical statistics
                 ex.single([&]() {
                     const double v[8] = {tot.cnt, tot.sum, tot.sq, tot.rcnt, tot.rsum, tot.rsq,
                                          double(tot.flags), 0.0};
-                    for (int k = 0; k < 8; ++k) { c.xl->stat[c.rank][k] = v[k]; c.xp->stat[c.rank][k] = v[k]; }
+                    for (int rk = 0; rk < C::CL; ++rk) {
+                        Xchg *x = X_of<C>(c, rk);
+                        for (int k = 0; k < 8; ++k) x->stat[c.rank][k] = v[k];
+                    }
                 });
                 ex.cluster_sync();
                 ex.single([&]() {
                     StatPartial t = stat_zero();
-                    for (int rk = 0; rk < 2; ++rk) {
+                    for (int rk = 0; rk < C::CL; ++rk) {
                         const double *v = c.xl->stat[rk];
                         t.cnt += v[0]; t.sum += v[1]; t.sq += v[2];
                         t.rcnt += v[3]; t.rsum += v[4]; t.rsq += v[5]; t.flags |= int(v[6]);
@@ -1208,21 +1265,25 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
     }
 
     // ---- argmax over the interlaced surface + 5x5 quadratic fit ----------
-    if (C::CL == 2) {
-        // hand my best sample and my status bits to rank 0 (and vice versa)
-        ex.single([&]() {
-            c.xl->bestv[c.rank] = ps->best.v; c.xp->bestv[c.rank] = ps->best.v;
-            c.xl->besti[c.rank] = ps->best.idx; c.xp->besti[c.rank] = ps->best.idx;
-            c.xl->status[c.rank] = ps->status; c.xp->status[c.rank] = ps->status;
-            c.xl->det[c.dslot ^ 1][0] = 0u; c.xl->det[c.dslot ^ 1][1] = 0u;   // next pair's slot
+    if (C::CL > 1) {
+        // hand my best sample and my status bits to every CTA of the cluster
+        ex.parts(C::CL, [&](int rk) {
+            Xchg *x = X_of<C>(c, rk);
+            x->bestv[c.rank] = ps->best.v;
+            x->besti[c.rank] = ps->best.idx;
+            x->status[c.rank] = ps->status;
+            if (rk == 0) { c.xl->det[c.dslot ^ 1][0] = 0u; c.xl->det[c.dslot ^ 1][1] = 0u; }   // next pair's slot
         });
         // the cluster barrier is a release/acquire fence at cluster scope: my part of
         // the surface (global memory) is visible to rank 0 after it
         ex.cluster_sync();
         ex.single([&]() {
-            Best o; o.v = c.xl->bestv[c.rank ^ 1]; o.idx = c.xl->besti[c.rank ^ 1];
-            if (best_better(o, ps->best)) ps->best = o;
-            ps->status |= c.xl->status[c.rank ^ 1];
+            for (int rk = 0; rk < C::CL; ++rk) {
+                if (rk == c.rank) continue;
+                Best o; o.v = c.xl->bestv[rk]; o.idx = c.xl->besti[rk];
+                if (best_better(o, ps->best)) ps->best = o;
+                ps->status |= c.xl->status[rk];
+            }
         });
     }
     if (C::CL == 1 || c.rank == 0) {

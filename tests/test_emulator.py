@@ -1,0 +1,124 @@
+"""CPU test of the CUDA pass sequence through the host emulator (tools/host_emu.cu: the
+SAME engine source, spx_cc_engine.cuh, compiled with g++ and run serially; thread-block
+clusters are emulated with one host thread per CTA and a pthread barrier).  It keeps the
+index arithmetic, the cluster hand-off protocols (2 / 4 / 8 CTAs per pair, DSMEM row
+split, mirrored R rows) and the statistics-free NCC path checkable without a GPU, and
+re-runs the passes with permuted thread orders: a pass whose result depends on the order
+has an intra-pass data hazard (the stand-in for compute-sanitizer racecheck, which is
+closed on this pool).  The emulator is test infrastructure; the product never runs it."""
+import os
+import shutil
+import struct
+import subprocess
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import subpixal_oracle as orc
+
+EXE = os.path.join("/tmp", "spx_host_emu_%d" % os.getuid())
+
+
+@pytest.fixture(scope="module")
+def emu():
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    src = os.path.join(ROOT, "tools", "host_emu.cu")
+    deps = [src] + [os.path.join(ROOT, "subpixal_b200", "csrc", f)
+                    for f in os.listdir(os.path.join(ROOT, "subpixal_b200", "csrc"))]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.check_call([gxx, "-std=c++17", "-DSPX_HOST_EMU", "-O1", "-x", "c++", "-o", EXE,
+                               src, "-lpthread"])
+
+    def run(stacks, cc_type, no_icc=0, env=None):
+        n, _, ny, nx = stacks.shape
+        base = "/tmp/spx_emu_%d" % os.getpid()
+        with open(base + ".in", "wb") as f:
+            f.write(struct.pack("5i", n, ny, nx, cc_type, no_icc))
+            f.write(np.ascontiguousarray(stacks, dtype=np.float32).tobytes())
+        subprocess.check_call([EXE, base + ".in", base + ".out"], env=dict(os.environ, **(env or {})))
+        buf = open(base + ".out", "rb").read()
+        o = 0
+        sh = np.frombuffer(buf, np.float64, 2 * n, o).reshape(n, 2).copy(); o += 16 * n
+        pk = np.frombuffer(buf, np.int32, n, o).copy(); o += 4 * n
+        st = np.frombuffer(buf, np.int32, n, o).copy(); o += 4 * n
+        icc = np.frombuffer(buf, np.float32, n * 4 * ny * nx, o).reshape(n, 2 * ny, 2 * nx).copy()
+        os.remove(base + ".in"); os.remove(base + ".out")
+        return sh, pk, st, icc
+    return run
+
+
+def _oracle(stack, t):
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        return orc.find_displacement(*stack, cc_type=t, full_output=True)
+
+
+# (pairs, ny, nx, masked): single-CTA classes, the 2-CTA (128), 4-CTA (170) and 8-CTA (256)
+# cluster classes, full-tile fast paths and ragged shapes of each
+CASES = [(2, 32, 32, False), (2, 64, 64, False), (1, 20, 37, True), (1, 5, 7, False),
+         (1, 128, 128, False), (1, 100, 90, True), (1, 170, 170, False), (1, 150, 129, False),
+         (1, 256, 256, False), (1, 200, 256, True)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d" % (c[1], c[2]))
+def test_emulated_passes_match_the_oracle(emu, case):
+    n, ny, nx, masked = case
+    stacks, _ = orc.random_pairs(n, ny, nx, seed=1000 * ny + nx, masked=masked)
+    for t, name in enumerate(("CC", "NCC", "ZNCC")):
+        if max(ny, nx) > 128 and name == "CC":
+            continue                                    # keep the CPU suite short
+        sh, pk, st, icc = emu(stacks, t)
+        for k in range(n):
+            dx, dy, ricc, _ = _oracle(stacks[k], name)
+            assert int(np.argmax(ricc)) == pk[k] and st[k] == 0
+            assert abs(sh[k, 0] - dx) < 5e-5 and abs(sh[k, 1] - dy) < 5e-5
+            assert np.linalg.norm(icc[k] - ricc) <= 1e-5 * np.linalg.norm(ricc)
+
+
+@pytest.mark.parametrize("case", [(1, 64, 64, False), (1, 128, 128, False), (1, 170, 160, False),
+                                  (1, 256, 256, False)], ids=lambda c: "%dx%d" % (c[1], c[2]))
+def test_results_do_not_depend_on_the_thread_order(emu, case):
+    """Reversed / warp-interleaved execution order inside every pass gives bit-identical
+    results: no intra-pass hazards (in-place row stage, cluster row split)."""
+    n, ny, nx, masked = case
+    stacks, _ = orc.random_pairs(n, ny, nx, seed=77 + ny, masked=masked)
+    ref = emu(stacks, 2)
+    for order in ("1", "2"):
+        got = emu(stacks, 2, env={"SPX_EMU_ORDER": order})
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got)), order
+
+
+def test_cluster_and_slab_forms_of_the_large_classes_agree(emu):
+    """170 / 256 px: the cluster forms (shared memory, DSMEM) and the global-slab forms run
+    the same arithmetic in the same order - bit-identical results."""
+    for ny, nx in ((170, 170), (256, 256)):
+        stacks, _ = orc.random_pairs(1, ny, nx, seed=ny)
+        a = emu(stacks, 1)
+        b = emu(stacks, 1, env={"SPX_EMU_SLAB": "1"})
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), (ny, nx)
+
+
+def test_statistics_free_ncc_path(emu):
+    """No surface requested + NCC: the statistics sweep is skipped when both standard
+    deviations are provably positive; degenerate inputs fall back to the exact path."""
+    for n, ny, nx in ((3, 32, 32), (2, 64, 64), (1, 128, 128), (1, 48, 40), (1, 256, 256)):
+        stacks, _ = orc.random_pairs(n, ny, nx, seed=5 * ny + nx, masked=(ny == 48))
+        lazy = emu(stacks, 1, no_icc=1)
+        exact = emu(stacks, 1, no_icc=0)
+        assert np.array_equal(lazy[1], exact[1]) and np.array_equal(lazy[2], exact[2])
+        assert np.max(np.abs(lazy[0] - exact[0])) < 5e-6
+    base, _ = orc.random_pairs(1, 32, 32, seed=3)
+    cases = []
+    c = base[0].copy(); c[1:] = 0; c[1:, 5, 5] = 3.0; cases.append(c)      # one pixel per phase
+    c = base[0].copy(); c[1:] = 2.5; cases.append(c)                       # constant phases
+    c = base[0].copy(); c[0] = 7.0; cases.append(c)                        # constant ref
+    c = base[0].copy(); c[1:3] = 0; cases.append(c)                        # first phase pair empty
+    cases.append(base[0] * np.float32(1e15))                               # huge values
+    c = base[0].copy(); c[2, 4, 4] = np.nan; cases.append(c)               # NaN in a phase
+    stacks = np.stack(cases)
+    lazy, exact = emu(stacks, 1, no_icc=1), emu(stacks, 1, no_icc=0)
+    assert np.array_equal(lazy[0], exact[0], equal_nan=True) and np.array_equal(lazy[1], exact[1])

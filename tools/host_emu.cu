@@ -56,11 +56,11 @@ template <class C>
 void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts, int *peak,
          int *status, float *icc) {
     constexpr int CL = C::CL;
-    std::vector<cf> W[2], S[2], R[2];
-    std::vector<uint16_t> rrow[2];
-    PairState ps[2];
-    Xchg xc[2];
-    Ctx<C> c[2];
+    std::vector<cf> W[kMaxCluster], S[kMaxCluster], R[kMaxCluster];
+    std::vector<uint16_t> rrow[kMaxCluster];
+    PairState ps[kMaxCluster];
+    Xchg xc[kMaxCluster];
+    Ctx<C> c[kMaxCluster];
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, nullptr, CL);
     for (int rk = 0; rk < CL; ++rk) {
@@ -73,10 +73,10 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
         c[rk].xl = &xc[rk];
         for (int k = 0; k < 4; ++k) (&xc[rk].det[0][0])[k] = 0u;
     }
-    for (int rk = 0; rk < CL; ++rk) {
-        c[rk].Wpeer = CL == 2 ? W[rk ^ 1].data() : nullptr;
-        c[rk].xp = CL == 2 ? &xc[rk ^ 1] : nullptr;
-    }
+    for (int rk = 0; rk < CL; ++rk)
+        for (int o = 0; o < CL; ++o) {
+            c[rk].Wall[o] = W[o].data(); c[rk].Rall[o] = R[o].data(); c[rk].xall[o] = &xc[o];
+        }
     const size_t tile = size_t(ny) * nx;
     auto body = [&](int rk) {
         HostExec<C> ex;
@@ -95,9 +95,10 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
     if (CL == 1) {
         body(0);
     } else {
-        std::thread t1(body, 1);
+        std::vector<std::thread> th;
+        for (int rk = 1; rk < CL; ++rk) th.emplace_back(body, rk);
         body(0);
-        t1.join();
+        for (auto &t : th) t.join();
     }
     pthread_barrier_destroy(&bar);
 }
@@ -116,14 +117,18 @@ int main(int argc, char **argv) {
     std::vector<int> peak(n), status(n);
     std::vector<float> icc(size_t(n) * 4 * ny * nx);
     const int m = ny > nx ? ny : nx;
+    // 170 / 256 px classes: 4- / 8-CTA cluster forms by default, SPX_EMU_SLAB=1: global-slab forms
+    const bool slab = getenv("SPX_EMU_SLAB") && atoi(getenv("SPX_EMU_SLAB")) != 0;
     if (m <= 20) run<CcCfg<32, 4, 8, 20, 64, 12, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 32 && m <= 42) run<CcCfg<64, 8, 8, 42, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 64 && m <= 84) run<CcCfg<128, 8, 16, 84, 512, 1, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
-    else if (m > 128 && m <= 170) run<CcCfg<256, 16, 16, 170, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m > 128 && m <= 170 && slab) run<CcCfg<256, 16, 16, 170, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m > 128 && m <= 170) run<CcCfg<256, 16, 16, 170, 512, 1, true, true, true, 4>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, true, true, EMU128_INPLACE, 2>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
-    else run<CcCfg<384, 24, 16, 256, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (slab) run<CcCfg<384, 24, 16, 256, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else run<CcCfg<384, 24, 16, 256, 384, 1, true, true, true, 8>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     f = fopen(argv[2], "wb");
     fwrite(shifts.data(), 8, shifts.size(), f);
     fwrite(peak.data(), 4, n, f);

@@ -30,13 +30,13 @@ def make_scene(n_src, height, width, cutout, seed):
     }
 
 
-def misalign(scene, shift=(0.37, -0.21), rot=5e-5):
-    """Positions of the sources in the reference frames: rotation about the
-    frame centre plus a shift.  Returns (x', y') and the per-source true shift
-    of the reference relative to the image."""
+def misalign(scene, shift=(0.37, -0.21), rot=5e-5, scale=1.0):
+    """Positions of the sources in the reference frames: rotation (and isotropic
+    scale) about the frame centre plus a shift.  Returns (x', y') and the per-source
+    true shift of the reference relative to the image."""
     cx, cy = (scene["width"] - 1) / 2.0, (scene["height"] - 1) / 2.0
     dx, dy = scene["x"] - cx, scene["y"] - cy
-    c, s = math.cos(rot), math.sin(rot)
+    c, s = scale * math.cos(rot), scale * math.sin(rot)
     xr = cx + c * dx - s * dy + shift[0]
     yr = cy + s * dx + c * dy + shift[1]
     return xr, yr, np.stack([xr - scene["x"], yr - scene["y"]], axis=1)
@@ -67,10 +67,10 @@ def render(scene, xs, ys, device, half=21, chunk=4096):
     return out.reshape(H, W).to(torch.float32)
 
 
-def make_frames(scene, device, shift=(0.37, -0.21), rot=5e-5, noise=1.0):
+def make_frames(scene, device, shift=(0.37, -0.21), rot=5e-5, noise=1.0, scale=1.0):
     """[5, H, W] float32: image frame + the four reference-phase frames."""
     H, W = scene["height"], scene["width"]
-    xr, yr, truth = misalign(scene, shift, rot)
+    xr, yr, truth = misalign(scene, shift, rot, scale)
     frames = torch.empty((5, H, W), dtype=torch.float32, device=device)
     gen = torch.Generator(device="cpu").manual_seed(int(scene["seed"]) + 17)
     frames[0] = render(scene, scene["x"], scene["y"], device)

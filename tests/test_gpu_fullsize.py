@@ -90,6 +90,32 @@ def test_config3_128_masked():
     assert np.all(sh.cpu().numpy()[bad] == np.array([-63.0, -63.0]))
 
 
+def test_config3_disc_mask_500_pairs_per_type():
+    """Config 3 inputs as bench.py's `sizes["128"]` block builds them:
+    128x128 pairs, phase tiles zero outside a disc of radius 0.4 N plus 0.1 % zeroed phase
+    pixels; 500 pairs per cc_type against the oracle (shift, peak index, near ties)."""
+    from subpixal_b200 import batch, synthetic as syn
+    stack, _ = syn.make_pair_pool(1500, 128, 20243, "cuda", disc_mask=True, zero_frac=1e-3)
+    assert float((stack[:, 1:] == 0).float().mean()) > 0.45          # the mask is there
+    host = stack[:500].cpu().numpy()
+    for t in ("NCC", "ZNCC"):
+        sh, pk, st, _ = batch.cc_fit_stack(stack, t)
+        sh, pk = sh.cpu().numpy(), pk.cpu().numpy()
+        assert np.all(np.isfinite(sh)) and np.all((st.cpu().numpy() & 0x3f) == 0)
+        worst, ties = 0.0, 0
+        for k in range(500):
+            with warnings.catch_warnings(), np.errstate(all="ignore"):
+                warnings.simplefilter("ignore")
+                dx, dy, icc, _ = orc.find_displacement(*host[k], cc_type=t, full_output=True)
+            if int(np.argmax(icc)) != int(pk[k]):
+                srt = np.sort(icc.ravel())
+                assert (srt[-1] - srt[-2]) <= 1e-5 * abs(srt[-1]), (t, k)
+                ties += 1
+                continue
+            worst = max(worst, abs(sh[k, 0] - dx), abs(sh[k, 1] - dy))
+        assert worst < 1e-3 and worst < 1e-4 and ties <= 5, (t, worst, ties)
+
+
 def test_config4_workflow_recovers_frame_transform():
     """Reduced config 4: shifts of 20 000 sources on a 4096x4096 frame feed the
     linear-transformation fit, which must recover the injected misalignment."""

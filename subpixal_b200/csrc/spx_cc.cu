@@ -8,6 +8,7 @@
 // (dx, dy) pair goes back to HBM unless the caller asks for the surface.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -133,9 +134,13 @@ template <class C> struct Layout {
     // shared memory carve-up (bytes); everything 16-byte aligned
     static constexpr size_t off_ps = 0;
     static constexpr size_t off_red = 256;                       // reductions
-    static constexpr size_t red_bytes = 32 * 8 * 8;              // [32 warps][8] doubles
-    static constexpr size_t off_xchg = off_red + red_bytes;       // Xchg (cluster mode)
-    static constexpr size_t off_rrow = off_xchg + 640;
+    // [NW][8] doubles (statistics); the argmax reduction keeps its indices at byte 256
+    static constexpr size_t red_bytes = C::NW * 64 > 512 ? C::NW * 64 : 512;
+    static constexpr size_t off_xchg = off_red + red_bytes;       // Xchg (whole only in cluster mode)
+    static constexpr size_t xchg_bytes = C::CL > 1 ? 640 : 64;
+    static constexpr size_t off_win = off_xchg + xchg_bytes;      // FitWin (surface kept in W)
+    static constexpr size_t win_bytes = SurfaceInW<C>::value ? 832 : 0;
+    static constexpr size_t off_rrow = off_win + win_bytes;
     static constexpr size_t rrow_bytes = ((C::RH * 2 + 15) / 16) * 16;
     static constexpr size_t off_xrow = off_rrow + rrow_bytes;
     static constexpr size_t xrow_bytes = 0;
@@ -144,7 +149,8 @@ template <class C> struct Layout {
     static constexpr size_t off_R = off_W + (C::W_SMEM ? C::W_ELEMS * 8 : 0);
     static constexpr size_t total = off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0);
     static_assert(sizeof(PairState) <= 256, "PairState must fit its slot");
-    static_assert(sizeof(Xchg) <= 640, "Xchg must fit its slot");
+    static_assert(sizeof(Xchg) <= 640 && offsetof(Xchg, stat) <= 64, "Xchg must fit its slot");
+    static_assert(sizeof(FitWin) <= 832, "FitWin must fit its slot");
 };
 
 __device__ __forceinline__ Best warp_best(Best b) {
@@ -206,7 +212,8 @@ struct DevExec {
         if (int(threadIdx.x) < n) f(int(threadIdx.x));
         __syncthreads();
     }
-    template <class F> __device__ __forceinline__ void reduce_best_into(Best *dst, F f) {
+    template <class F, class A>
+    __device__ __forceinline__ void reduce_best_into(Best *dst, F f, A after) {
         Best b = warp_best(f(int(threadIdx.x)));
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         float *redf = reinterpret_cast<float *>(red);
@@ -218,6 +225,8 @@ struct DevExec {
             if (lane < C::NW) { t.v = redf[lane]; t.idx = redi[lane]; }
             t = warp_best(t);
             if (lane == 0 && best_better(t, *dst)) *dst = t;
+            __syncwarp();
+            after(lane);
         }
         __syncthreads();
     }
@@ -329,6 +338,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
     c.rank = rank;
     c.col_lo = rank * C::NXL;
     c.xl = reinterpret_cast<Xchg *>(smem + L::off_xchg);
+    c.win = reinterpret_cast<FitWin *>(smem + L::off_win);
 
     DevExec<C> ex;
     ex.red = reinterpret_cast<double *>(smem + L::off_red);
@@ -397,7 +407,8 @@ template <class C>
 static SlabPlan plan_slab(int ny, int nx, bool want_icc) {
     SlabPlan s;
     size_t o = 0;
-    s.off_icc = o; if (!want_icc) o += align_up(size_t(16) * ny * nx, 256);
+    // surface scratch: only when nobody asked for the surface AND it cannot stay in W
+    s.off_icc = o; if (!want_icc && !SurfaceInW<C>::value) o += align_up(size_t(16) * ny * nx, 256);
     s.off_w = o;   if (!C::W_SMEM) o += align_up(C::W_ELEMS * 8, 256);
     s.off_r = o;   if (!C::R_SMEM) o += align_up(C::R_ELEMS * 8, 256);
     s.bytes = align_up(o, 256);

@@ -140,6 +140,8 @@ struct PairState {
     int interior;          // box entirely inside the source image
     int report;            // status bits of the tiles whose NaN/Inf are reported
     int status;
+    int keep, in_w;        // surface kept in W (see SurfaceInW); the phase pair W holds now
+    int ysh, cout;         // W row of lag row 0, W column of lag column 0
     Best best;             // running argmax over the interlaced surface
 };
 
@@ -147,10 +149,7 @@ struct PairState {
 // EVERY copy, then a cluster barrier, then reads its local copy).
 constexpr int kMaxCluster = 8;
 struct Xchg {
-    double stat[kMaxCluster][8];
-    float bestv[kMaxCluster];
-    int besti[kMaxCluster];
-    int status[kMaxCluster];
+    // (det comes first: single-CTA configurations only allocate the first 64 bytes)
     // degeneracy detector of the statistics-free NCC path (lazy_decide): det[s][0] evidence
     // bits (1: phases, 2: reference), det[s][1] bits of the largest |pixel| seen; in cluster
     // mode both CTAs update both copies with atomics.  Two slots, used by alternate pairs:
@@ -158,6 +157,37 @@ struct Xchg {
     // the current pair - the only window in which the peer can neither still read it
     // (previous pair) nor already write it (next pair).
     unsigned det[2][2];
+    double stat[kMaxCluster][8];
+    float bestv[kMaxCluster];
+    int besti[kMaxCluster];
+    int status[kMaxCluster];
+};
+
+// Surface kept on chip.  When the caller does not ask for the surface (and one CTA holds
+// W), IC2 writes its outputs back IN PLACE into the W slots it read - W row n, column l
+// then holds the complex sample (C_a0, C_a1)(lag row n - ysh, lag column l) of the phase
+// pair just finished - and only the argmax runs over them.  The 5x5 fit needs samples of
+// BOTH phase pairs (even / odd surface rows): the second pair's are still in W at the end;
+// of the first pair a 7x7 window of complex samples around ITS best sample is saved before
+// the second pair overwrites W.  The four lattices of one source peak within a sample of
+// each other, so the window almost always covers the fit box; when it does not (global
+// best far from the first pair's best), the needed samples of the second pair are saved
+// the same way and the first pair is transformed once more.
+//
+// Measured (B200, stack mode, A/B on one box): keeping the surface in W is 1.7 % slower at
+// 64 px and 4 % slower at 20 / 32 px than writing it to the per-CTA slab in global memory,
+// which stays L2 resident (stores carry an evict-last policy): shared-memory bandwidth is
+// what binds these kernels, the L2 has slack.  So the slab is the default and
+// -DSPX_KEEP_SURFACE=1 builds the on-chip form (tests/test_emulator.py keeps it alive).
+#if defined(SPX_KEEP_SURFACE) && SPX_KEEP_SURFACE
+template <class C> struct SurfaceInW { static constexpr bool value = C::W_SMEM && C::CL == 1; };
+#else
+template <class C> struct SurfaceInW { static constexpr bool value = false; };
+#endif
+constexpr int kWinR = 3, kWinN = 2 * kWinR + 1;
+struct FitWin {
+    cf v[2][kWinN][kWinN];     // [phase pair][lattice row - k0][lattice column - l0]
+    int k0[2], l0[2];
 };
 
 template <class C>
@@ -170,6 +200,7 @@ struct Ctx {
     int rank, col_lo, n_rrow;
     int dslot;             // detector slot of the current pair (alternates, see Xchg)
     Xchg *xl;              // local exchange block
+    FitWin *win;           // fit-sample windows (SurfaceInW configurations)
 #ifdef SPX_HOST_EMU        // the emulator keeps a table of every CTA's buffers
     cf *Wall[kMaxCluster], *Rall[kMaxCluster];
     Xchg *xall[kMaxCluster];
@@ -719,6 +750,30 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
     }
 }
 
+// Store two surface samples.  `scratch`: the destination is the per-CTA scratch slab that
+// only the fit reads back (nobody asked for the surface): the store carries an L2
+// evict-last policy so that the streaming tile loads do not push the slab out to HBM.
+SPX_HD unsigned long long l2_evict_last_policy() {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+#else
+    return 0ull;
+#endif
+}
+SPX_HD void st_surface(float *p, float v0, float v1, bool scratch, unsigned long long pol) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    if (scratch) {
+        asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;"
+                     :: "l"(p), "f"(v0), "f"(v1), "l"(pol) : "memory");
+        return;
+    }
+#endif
+    (void)scratch; (void)pol;
+    *reinterpret_cast<cf *>(p) = cmake(v0, v1);
+}
+
 // IC2: E1-point inverse FFT over k1; outputs n = E2*n1+n2 < ny are the lags
 // n - yc of phases (a=0, b) [real part] and (a=1, b) [imaginary part].
 // Inputs were sanitised, so the surface is finite and a plain ">" scan in
@@ -731,6 +786,9 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
     const int nchunk = (nx + 31) >> 5;
     const int w2 = 2 * ps.nx;
     float *icc = c.icc;
+    const bool keep = ps.keep != 0;              // nobody asked for the surface
+    // (the 80-register classes have no room for the 64-bit policy across the item loop)
+    const unsigned long long pol = C::T * C::MINB <= 512 ? l2_evict_last_policy() : 0ull;
     const int cbase = 2 * c.col_lo;              // my columns start at surface column 2*col_lo
     const WBases<C> wr = w_bases<C>(c);
     Best best = best_init();
@@ -756,7 +814,10 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
             if (unsigned(C::E2 * n1 + nb) < unsigned(ny)) {
                 const float v0 = x[n1].x, v1 = x[n1].y;
                 const int idx = idx0 + n1 * (2 * C::E2) * w2;
-                *reinterpret_cast<cf *>(icc + idx) = cmake(v0, v1);
+                if (SurfaceInW<C>::value && keep)       // in place: the slot this thread read
+                    c.W[(n1 * C::E2 + n2) * C::WP + gl] = cmake(v0, v1);
+                else
+                    st_surface(icc + idx, v0, v1, keep && C::T * C::MINB <= 512, pol);
                 if (v0 > bv) { bv = v0; bi = idx; }
                 if (v1 > bv) { bv = v1; bi = idx + 1; }
             }
@@ -1082,6 +1143,7 @@ SPX_HD void fill_state(PairState &ps, const PairJob &job, int part) {
     ps.yc = (job.ny - 1) / 2; ps.xc = (job.nx - 1) / 2;
     ps.cc_type = job.cc_type; ps.flags = job.flags;
     ps.mu = 0.f; ps.mu_ref = 0.f; ps.rscale = 1.f;
+    ps.keep = job.patch_icc ? 0 : 1; ps.in_w = -1; ps.ysh = 0; ps.cout = 0;
     ps.ylo = job.y1 < 0 ? -job.y1 : 0;
     ps.yhi = job.y1 + job.ny > job.H ? job.H - job.y1 : job.ny;
     ps.xlo = job.x1 < 0 ? -job.x1 : 0;
@@ -1097,15 +1159,102 @@ SPX_HD void fill_state(PairState &ps, const PairJob &job, int part) {
 }
 
 // --------------------------------------------------------------------------
+// fit samples of a surface that was kept in W (SurfaceInW)
+// --------------------------------------------------------------------------
+// part t of kWinN*kWinN: copy sample (kc - kWinR + t / kWinN, lc - kWinR + t % kWinN) of the
+// phase pair now in W into window w
+template <class C>
+SPX_HD void save_window(const Ctx<C> &c, int w, int kc, int lc, int t, int ysh, int cout) {
+    const PairState &ps = *c.ps;
+    const int dk = t / kWinN, dl = t - dk * kWinN;
+    const int k = kc - kWinR + dk, l = lc - kWinR + dl;
+    if (t == 0) { c.win->k0[w] = kc - kWinR; c.win->l0[w] = lc - kWinR; }
+    if (k >= 0 && k < ps.ny && l >= 0 && l < ps.nx)
+        c.win->v[w][dk][dl] = c.W[(k + ysh) * C::WP + l + cout];
+}
+// surface sample at flat index idx of the (2ny, 2nx) surface
+template <class C>
+SPX_HD float kept_sample(const Ctx<C> &c, int idx) {
+    const PairState &ps = *c.ps;
+    const int w2 = 2 * ps.nx;
+    const int jj = idx / w2, ii = idx - jj * w2;
+    const int b = jj & 1, k = jj >> 1, l = ii >> 1;
+    const cf v = (b == ps.in_w) ? c.W[(k + ps.ysh) * C::WP + l + ps.cout]
+                                : c.win->v[b][k - c.win->k0[b]][l - c.win->l0[b]];
+    return (ii & 1) ? v.y : v.x;
+}
+// do the samples of phase pair b that the fit box needs lie inside window b?
+template <class C>
+SPX_HD bool window_covers(const Ctx<C> &c, const PeakGeom &g, int b) {
+    if (g.mode != 0) return true;                       // no fit, no samples
+    const int jlo = g.y1 + ((g.y1 & 1) != b), jhi = g.y1 + 4 - (((g.y1 + 4) & 1) != b);
+    const int klo = jlo >> 1, khi = jhi >> 1, llo = g.x1 >> 1, lhi = (g.x1 + 4) >> 1;
+    const int k0 = c.win->k0[b], l0 = c.win->l0[b];
+    return klo >= k0 && khi < k0 + kWinN && llo >= l0 && lhi < l0 + kWinN;
+}
+
+// --------------------------------------------------------------------------
 // reference transform + the two phase pairs (see the data flow at the top)
 // --------------------------------------------------------------------------
-// lazy: statistics-free NCC attempt; returns false (after a C1 pass over image tiles) when
-// the detector could not prove the normalisation well defined.
 #ifdef SPX_LAZY_NODETECT                 // developer knob: cost of the detector (results unchecked)
 constexpr int kLazyDetect = 0;
 #else
 constexpr int kLazyDetect = 2;
 #endif
+
+// One phase pair (round IT: 0 / 1 = first / second pair, 2 = the first pair once more):
+// C1 C2 X1 X2 X3 IC1 IC2 + argmax.  Returns false when the statistics-free attempt has to
+// be abandoned (lazy_decide).
+template <class C, bool FAST, bool CHECK, class Ex>
+SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, int yoff, int xoff,
+                       int ysh, int xsh, int cin, int cout) {
+    PairState *ps = c.ps;
+    const int b = IT & 1;
+    const int lz = (lazy && IT < 2) ? (b == 0 ? kLazyDetect : 1) : 0;
+    ex.par([&](int tid) {
+        const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin, lz);
+        if (fl) ex.or_status(&ps->status, fl);
+    });
+    if (C::CL > 1) ex.cluster_sync();       // the peer's half of my rows has arrived
+    // (the detector keys of both CTAs are complete after this barrier; every thread
+    // evaluates the same few comparisons, so the branch is uniform)
+    if (lazy && IT < 2 && !lazy_decide(c.xl->det[c.dslot], b == 0)) return false;
+    ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
+    if (C::INPLACE) {
+        ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
+        ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
+        ex.par([&](int tid) { x3_pass<C>(c, tid, 0, C::NCHUNK, xsh); });
+    } else {
+        for (int k = 0; k < C::NCHUNK; ++k) {
+            if (!C::DIRECT) ex.par([&](int tid) { stage_in<C, false>(c, tid, k, xoff); });
+            ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff); });
+            ex.par([&](int tid) { x2_pass<C>(c, tid, k, k + 1); });
+            ex.par([&](int tid) { x3_pass<C>(c, tid, k, k + 1, xsh); });
+            if (!C::DIRECT) ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
+        }
+    }
+    ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });
+    if (C::CL > 1) ex.cluster_sync();       // the peer's rows hold their lags: IC2 may read them
+    // W now holds this pair's surface (keep).  After the first pair the warp that finishes
+    // the argmax also saves the window around the best sample of that pair, before the
+    // barrier that lets the next C1 pass overwrite W.
+    ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh, cout); },
+                        [&](int lane) {
+        if (!keep) return;
+        if (lane == 0) { ps->in_w = b; ps->ysh = ysh; ps->cout = cout; }
+        if (IT != 0) return;
+        const int kc = (ps->best.idx / (2 * ps->nx)) >> 1, lc = (ps->best.idx % (2 * ps->nx)) >> 1;
+        for (int t = lane; t < kWinN * kWinN; t += 32) save_window<C>(c, 0, kc, lc, t, ysh, cout);
+    });
+    // the peer must not start writing my rows (its next C1) while I still read
+    // them; after the second pair the exchange barrier of the peak stage does that
+    if (C::CL > 1 && b == 0) ex.cluster_sync();
+    return true;
+}
+
+// lazy: statistics-free NCC attempt; returns false (after a C1 pass over image tiles) when
+// the detector could not prove the normalisation well defined.
+
 template <class C, bool FAST, bool CHECK, class Ex>
 SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
     PairState *ps = c.ps;
@@ -1141,36 +1290,30 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
     if (C::CL > 1) ex.cluster_sync();           // I am done with W: the peer's next C1 may write it
 
     // ---- phase pairs: (im00, im10) -> even rows, (im01, im11) -> odd rows --
-    for (int b = 0; b < 2; ++b) {
-        const int lz = lazy ? (b == 0 ? kLazyDetect : 1) : 0;
-        ex.par([&](int tid) {
-            const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin, lz);
-            if (fl) ex.or_status(&ps->status, fl);
-        });
-        if (C::CL > 1) ex.cluster_sync();       // the peer's half of my rows has arrived
-        // (the detector keys of both CTAs are complete after this barrier; every thread
-        // evaluates the same few comparisons, so the branch is uniform)
-        if (lazy && !lazy_decide(c.xl->det[c.dslot], b == 0)) return false;
-        ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
-        if (C::INPLACE) {
-            ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
-            ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
-            ex.par([&](int tid) { x3_pass<C>(c, tid, 0, C::NCHUNK, xsh); });
-        } else {
-            for (int k = 0; k < C::NCHUNK; ++k) {
-                if (!C::DIRECT) ex.par([&](int tid) { stage_in<C, false>(c, tid, k, xoff); });
-                ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff); });
-                ex.par([&](int tid) { x2_pass<C>(c, tid, k, k + 1); });
-                ex.par([&](int tid) { x3_pass<C>(c, tid, k, k + 1, xsh); });
-                if (!C::DIRECT) ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
+    // Round 0 and 1 are the two pairs - ONE loop body with a runtime round (two specialised
+    // copies spill in the 64 px class and cost 7 %); round 2 repeats the first pair when
+    // its fit samples were not kept (see SurfaceInW) - rare, a cold second copy.
+    const bool keep = SurfaceInW<C>::value && ps->keep != 0;
+#if !defined(SPX_HOST_EMU)
+#pragma unroll 1
+#endif
+    for (int it = 0; it < 2; ++it)
+        if (!phase_pair<C, FAST, CHECK>(c, ex, it, lazy, keep, yoff, xoff, ysh, xsh, cin, cout))
+            return false;
+    if constexpr (SurfaceInW<C>::value) {
+        if (keep) {
+            const PeakGeom g = peak_geometry(*ps);      // ps->best is final: uniform decision
+            if (!window_covers<C>(c, g, 0)) {
+#ifdef SPX_HOST_EMU
+                if (getenv("SPX_EMU_COUNT")) fprintf(stderr, "fallback: third round\n");
+#endif
+                // keep the second pair's samples around the global best, then redo the first
+                ex.parts(kWinN * kWinN, [&](int t) {
+                    save_window<C>(c, 1, g.jmax >> 1, g.imax >> 1, t, ysh, cout);
+                });
+                phase_pair<C, FAST, CHECK>(c, ex, 2, false, keep, yoff, xoff, ysh, xsh, cin, cout);
             }
         }
-        ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });
-        if (C::CL > 1) ex.cluster_sync();       // the peer's rows hold their lags: IC2 may read them
-        ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh, cout); });
-        // the peer must not start writing my rows (its next C1) while I still read
-        // them; after the second pair the exchange barrier of the peak stage does that
-        if (C::CL > 1 && b == 0) ex.cluster_sync();
     }
     return true;
 }
@@ -1181,7 +1324,8 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
 //   single(f)       run f() on one thread, then barrier
 //   parts(n, f)     run f(0..n-1) on n different threads, then barrier
 //   reduce_stats(f) block reduction of f(tid); meaningful in the next single()
-//   reduce_best_into(dst, f)  block argmax of f(tid) merged into *dst, barrier
+//   reduce_best_into(dst, f, after)  block argmax of f(tid) merged into *dst, then
+//                   after(lane) on the 32 lanes of the warp that merged it, barrier
 //   warp_fit(lane_f, final_f) one warp: sum lane_f(lane) over 32 lanes, then
 //                   final_f(sum) on one lane, then barrier
 //   cluster_sync()  barrier over both CTAs of a cluster (CL == 2 only)
@@ -1291,7 +1435,10 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
         ex.warp_fit(
             [&](int lane) {
                 const PeakGeom g = peak_geometry(*ps);
-                return peak_lane(*ps, g, lane, [&](int i) { return ex.load_icc(icc + i); });
+                return peak_lane(*ps, g, lane, [&](int i) {
+                    if (SurfaceInW<C>::value && ps->keep) return kept_sample<C>(c, i);
+                    return ex.load_icc(icc + i);
+                });
             },
             [&](const FitSums &f) {
                 const PeakGeom g = peak_geometry(*ps);

@@ -54,23 +54,59 @@ class ResultGather(object):
     (``batch.cc_fit_*(..., table=gather.local)``), ``gather()`` sends them with one
     ``all_gather_into_tensor`` into ``self.full`` and returns VIEWS of it - no packing
     or unpacking kernels, no allocation per step.  Rows past a rank's own pair count
-    keep the NaN / -1 padding they were created with."""
+    keep the NaN / -1 padding they were created with.
 
-    def __init__(self, per_rank, world, device, group=None):
+    ``depth`` > 1 keeps a ring of buffer sets for pipelined batches: ``advance()`` moves to
+    the next set (waiting for the all-gather that last used it), ``gather(async_op=True)``
+    only enqueues the collective on NCCL's stream, so the all-gather of batch i overlaps
+    the kernel of batch i + 1; ``wait()`` joins everything outstanding."""
+
+    def __init__(self, per_rank, world, device, group=None, depth=1):
         self.per, self.world, self.group = int(per_rank), int(world), group
-        self.local = torch.empty((self.per, 4), dtype=torch.float64, device=device)
-        self.local[:, :2] = float("nan")
-        self.local[:, 2:] = -1.0
-        self.full = (torch.empty((self.world * self.per, 4), dtype=torch.float64, device=device)
-                     if self.world > 1 else self.local)
+        self._sets, self._works, self._cur = [], [], 0
+        for _ in range(max(1, int(depth))):
+            local = torch.empty((self.per, 4), dtype=torch.float64, device=device)
+            local[:, :2] = float("nan")
+            local[:, 2:] = -1.0
+            full = (torch.empty((self.world * self.per, 4), dtype=torch.float64, device=device)
+                    if self.world > 1 else local)
+            self._sets.append((local, full))
+            self._works.append(None)
 
-    def gather(self, n=None):
+    @property
+    def local(self):
+        return self._sets[self._cur][0]
+
+    @property
+    def full(self):
+        return self._sets[self._cur][1]
+
+    def advance(self):
+        """Switch to the next buffer set of the ring; returns its send buffer."""
+        self._cur = (self._cur + 1) % len(self._sets)
+        w = self._works[self._cur]
+        if w is not None:
+            w.wait()
+            self._works[self._cur] = None
+        return self.local
+
+    def wait(self):
+        for k, w in enumerate(self._works):
+            if w is not None:
+                w.wait()
+                self._works[k] = None
+
+    def gather(self, n=None, async_op=False):
         """All-gather ``self.local``; returns float64 views ``(shifts [n,2], peak [n],
-        status [n])`` of the gathered table (peak / status hold exact integers)."""
+        status [n])`` of the gathered table (peak / status hold exact integers).  With
+        ``async_op`` the views are valid after ``wait()`` (or ``advance()`` back to this set)."""
         if self.world > 1:
-            dist.all_gather_into_tensor(self.full, self.local, group=self.group)
-        n = self.full.shape[0] if n is None else n
-        return self.full[:n, :2], self.full[:n, 2], self.full[:n, 3]
+            w = dist.all_gather_into_tensor(self.full, self.local, group=self.group,
+                                            async_op=async_op)
+            self._works[self._cur] = w if async_op else None
+        full = self.full
+        n = full.shape[0] if n is None else n
+        return full[:n, :2], full[:n, 2], full[:n, 3]
 
     def __call__(self, shifts, peak, status):
         """Results that were NOT written through ``table=self.local`` (separate tensors):

@@ -40,6 +40,20 @@ def _worker(rank, world, port, n):
             assert torch.isnan(g.full[n:, :2]).all()
         sh3, _, _ = g(shifts, peak, status)                   # separate tensors -> copied in
         assert torch.equal(sh3[:n], sh)
+        # pipelined form: ring of buffer sets, asynchronous all-gathers
+        ring = d.ResultGather(per, world, torch.device("cpu"), depth=2)
+        outs = []
+        for step in range(5):
+            loc = ring.advance()
+            loc[:hi - lo, :2] = shifts + step
+            loc[:hi - lo, 2] = peak
+            loc[:hi - lo, 3] = status
+            outs.append((step, ring.gather(n, async_op=True)[0]))
+            if step >= 1:                                     # the previous step's table is still intact
+                ring._works[(ring._cur + 1) % 2].wait()
+                assert torch.equal(outs[step - 1][1], sh + (step - 1))
+        ring.wait()
+        assert torch.equal(outs[-1][1], sh + 4)
     finally:
         dist.destroy_process_group()
 

@@ -122,3 +122,36 @@ def test_statistics_free_ncc_path(emu):
     stacks = np.stack(cases)
     lazy, exact = emu(stacks, 1, no_icc=1), emu(stacks, 1, no_icc=0)
     assert np.array_equal(lazy[0], exact[0], equal_nan=True) and np.array_equal(lazy[1], exact[1])
+
+
+def _decoy_case(n, decoy, rng):
+    """A pair whose global peak lies on an odd surface row (second phase pair) far away
+    from the best sample of the first phase pair (a decoy present in image00 / image10
+    only): the fit samples of the first pair are then NOT in the window kept on chip."""
+    c = (n - 1) / 2.0
+    st = np.zeros((5, n, n), np.float32)
+    st[0] = 0.02 * rng.standard_normal((n, n)) + orc.gaussian_star(n, c, c, 2.0, amp=10.0)
+    for k, (a, b) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
+        im = orc.gaussian_star(n, c - 9.0 - a / 2, c - 7.5 - b / 2, 2.0, amp=30.0)
+        if b == 0:
+            im = im + orc.gaussian_star(n, c + 3.0 - a / 2, c + 3.0, 2.0, amp=decoy)
+        st[1 + k] = im
+    return st
+
+
+def test_surface_kept_in_shared_memory(emu):
+    """No surface requested: IC2 works in place, the fit reads W plus the saved 7x7 window
+    of the first phase pair - or repeats the first pair when the window misses."""
+    rng = np.random.default_rng(1)
+    for n in (32, 64, 42):
+        stacks = np.stack([_decoy_case(n, 29.8, rng), _decoy_case(n, 0.0, rng)])
+        for t, name in enumerate(("CC", "ZNCC", )):
+            t = {"CC": 0, "ZNCC": 2}[name]
+            kept = emu(stacks, t, no_icc=1)
+            full = emu(stacks, t, no_icc=0)
+            assert np.array_equal(kept[0], full[0]) and np.array_equal(kept[1], full[1])
+            assert np.array_equal(kept[2], full[2]) and np.all(kept[2] == 0)
+            for k in range(2):
+                dx, dy, ricc, _ = _oracle(stacks[k], name)
+                assert int(np.argmax(ricc)) == kept[1][k] and (kept[1][k] // (2 * n)) % 2 == 1
+                assert abs(kept[0][k, 0] - dx) < 5e-5 and abs(kept[0][k, 1] - dy) < 5e-5

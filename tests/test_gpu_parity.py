@@ -292,7 +292,8 @@ def test_cabi_error_codes():
                                 p, p, p, z, z, 0, z) == L.E_UNSUPPORTED
     assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 1, 2, 8, 0,
                                 p, p, p, z, z, 0, z) == L.E_UNSUPPORTED
-    assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 1, 8, 8, 0,
+    # a class that needs a workspace (170 px: W / R slab) without one
+    assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 1, 150, 150, 0,
                                 p, p, p, z, z, 0, z) == L.E_WORKSPACE
     assert lib.spx_cc_fit_stack(p, p, p, p, p, C.byref(strides), 0, 8, 8, 0,
                                 p, p, p, z, z, 0, z) == 0
@@ -427,3 +428,27 @@ def test_ncc_without_statistics_sweep():
     exact = batch.cc_fit_stack(dev, "NCC", want_icc=True)
     assert torch.equal(lazy[1], exact[1]) and torch.equal(lazy[2], exact[2])
     assert np.array_equal(lazy[0].cpu().numpy(), exact[0].cpu().numpy(), equal_nan=True)
+
+
+def test_surface_kept_on_chip_matches_requested_surface():
+    """Without a requested surface the kernel keeps it in a per-CTA scratch (the L2-resident
+    slab by default; with -DSPX_KEEP_SURFACE=1 in shared memory: in-place IC2, the fit reads
+    W plus a saved 7x7 window of the first phase pair, or repeats the first pair when the
+    global peak lies far from that pair's best sample): CC / ZNCC results must be
+    bit-identical to the run that writes the surface, incl. the far-peak case."""
+    from subpixal_b200 import batch
+    from test_emulator import _decoy_case
+    rng = np.random.default_rng(1)
+    for n in (20, 32, 42, 64, 84):
+        cases = [_decoy_case(n, 29.8, rng), _decoy_case(n, 0.0, rng), _decoy_case(n, 29.9, rng)]
+        extra, _ = orc.random_pairs(5, n, n, seed=n)
+        dev = torch.from_numpy(np.concatenate([np.stack(cases), extra])).cuda()
+        for t in ("CC", "ZNCC", "NCC"):
+            kept = batch.cc_fit_stack(dev, t)
+            full = batch.cc_fit_stack(dev, t, want_icc=True)
+            assert torch.equal(kept[1], full[1]) and torch.equal(kept[2], full[2]), (n, t)
+            if t == "NCC":
+                assert float((kept[0] - full[0]).abs().max()) < 5e-6
+            else:
+                assert torch.equal(kept[0], full[0]), (n, t)
+        assert n < 32 or int(kept[1][0]) // (2 * n) % 2 == 1     # the decoy case peaks on an odd row

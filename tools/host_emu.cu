@@ -6,6 +6,9 @@
 // in.bin : int32 n, ny, nx, cc_type, no_icc (1: surface not requested -> the
 //          statistics-free NCC path may run) ; float32 [n,5,ny,nx]
 // out.bin: float64 [n,2] shifts ; int32 [n] peak ; int32 [n] status ; float32 [n,2ny,2nx]
+#ifndef SPX_KEEP_SURFACE
+#define SPX_KEEP_SURFACE 1      // the emulator exercises the on-chip surface form (build knob of the product)
+#endif
 #include <pthread.h>
 #include <cstdio>
 #include <cstdlib>
@@ -35,8 +38,9 @@ struct HostExec {
         return tot;
     }
     template <class F> void parts(int n, F f) { for (int t = 0; t < n; ++t) f(t); }
-    template <class F> void reduce_best_into(Best *dst, F f) {
+    template <class F, class A> void reduce_best_into(Best *dst, F f, A after) {
         for (int t = 0; t < C::T; ++t) { Best b = f(t); if (best_better(b, *dst)) *dst = b; }
+        for (int l = 0; l < 32; ++l) after(l);
     }
     template <class LF, class FF> void warp_fit(LF lane_f, FF final_f) {
         FitSums tot = fit_zero();
@@ -60,6 +64,7 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
     std::vector<uint16_t> rrow[kMaxCluster];
     PairState ps[kMaxCluster];
     Xchg xc[kMaxCluster];
+    FitWin win[kMaxCluster];
     Ctx<C> c[kMaxCluster];
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, nullptr, CL);
@@ -70,7 +75,7 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
         c[rk].rrow = rrow[rk].data(); c[rk].ps = &ps[rk];
         c[rk].n_rrow = build_rrow<C>(rrow[rk].data(), rk);
         c[rk].rank = rk; c[rk].col_lo = rk * C::NXL;
-        c[rk].xl = &xc[rk];
+        c[rk].xl = &xc[rk]; c[rk].win = &win[rk];
         for (int k = 0; k < 4; ++k) (&xc[rk].det[0][0])[k] = 0u;
     }
     for (int rk = 0; rk < CL; ++rk)

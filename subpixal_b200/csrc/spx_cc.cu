@@ -7,6 +7,7 @@
 // large for one SM, in a per-CTA slab that stays L2 resident), and only the
 // (dx, dy) pair goes back to HBM unless the caller asks for the surface.
 #include <cooperative_groups.h>
+#include <cuda.h>               // CUtensorMap (types only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -33,6 +34,9 @@ struct CcParams {
     double *shifts; int *peak; int *status; float *icc_out;
     unsigned char *workspace; size_t slab_bytes;
     size_t off_icc, off_w, off_r;   // byte offsets inside a slab
+    // staged configurations, frame mode: one 2-D tensor map per frame (box NMAX x NMAX,
+    // out-of-bounds elements read as zero = Cutout 'fill' mode), in global memory
+    const CUtensorMap *tmap;
 };
 
 // ---- configurations (one per supported maximum cutout size) -----------------
@@ -98,6 +102,18 @@ using Cfg170 = CcCfg<256, 16, 16, 170, 512, 1, false, false>;              // W 
 #endif
 using Cfg32  = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32_MINB, true,  true,  true>;
 using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, true,  true,  true>;
+// TMA-staged forms of the two headline classes (tiles of the next pair land in shared memory
+// while the current pair is transformed): 20 KB / 80 KB more shared memory per CTA, hence
+// 4 instead of 6 CTAs per SM at 32 px and ONE CTA of 16 warps instead of two of 8 at 64 px.
+// Selected at run time by SPX_STAGE=1 for uniform full-size batches (see use_stage()).
+#ifndef SPX32S_MINB
+#define SPX32S_MINB 4
+#endif
+#ifndef SPX64S_T
+#define SPX64S_T 512
+#endif
+using Cfg32S = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32S_MINB, true, true, true, 1, true>;
+using Cfg64S = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64S_T, 1, true, true, true, 1, true>;
 #ifndef SPX128_CLUSTER
 #define SPX128_CLUSTER 1
 #endif
@@ -147,7 +163,10 @@ template <class C> struct Layout {
     static constexpr size_t off_S = off_xrow + xrow_bytes;
     static constexpr size_t off_W = off_S + C::S_ELEMS * 8;
     static constexpr size_t off_R = off_W + (C::W_SMEM ? C::W_ELEMS * 8 : 0);
-    static constexpr size_t total = off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0);
+    // staged tiles [5][NMAX][NMAX] float (128-byte aligned for the TMA) + their mbarrier
+    static constexpr size_t off_tiles = (off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0) + 127) / 128 * 128;
+    static constexpr size_t off_mbar = off_tiles + C::TILE_BYTES;
+    static constexpr size_t total = C::STAGE ? off_mbar + 16 : off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0);
     static_assert(sizeof(PairState) <= 256, "PairState must fit its slot");
     static_assert(sizeof(Xchg) <= 640 && offsetof(Xchg, stat) <= 64, "Xchg must fit its slot");
     static_assert(sizeof(FitWin) <= 832, "FitWin must fit its slot");
@@ -246,6 +265,49 @@ struct DevExec {
         }
         __syncthreads();
     }
+    // ---- staged tiles (C::STAGE): TMA -> shared memory, completion on an mbarrier --------
+    unsigned mbar, tiles;            // shared-memory addresses
+    unsigned parity;                 // phase of the current pair's tiles
+    const CcParams *prm;
+    int next_pair;                   // pair whose tiles tiles_release() stages (-1: none)
+
+    __device__ __forceinline__ void tiles_issue(int p) {        // one thread
+        if (prm->boxes) {
+            // frame mode: five boxes of (NMAX + 4) x NMAX pixels starting at column x1 & ~3
+            constexpr unsigned bytes = unsigned(C::TILE_BYTES);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         :: "r"(mbar), "r"(bytes) : "memory");
+            const int4 b = __ldg(reinterpret_cast<const int4 *>(prm->boxes) + p);
+            const int xa = b.x & ~3;
+#pragma unroll
+            for (int s = 0; s < 5; ++s)
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                             " [%0], [%1, {%2, %3}], [%4];"
+                             :: "r"(tiles + s * unsigned(C::TILE_BYTES / 5)),
+                                "l"(reinterpret_cast<unsigned long long>(prm->tmap + s)),
+                                "r"(xa), "r"(b.y), "r"(mbar) : "memory");
+        } else {
+            constexpr unsigned bytes = unsigned(20 * C::NMAX * C::NMAX);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         :: "r"(mbar), "r"(bytes) : "memory");
+            const float *src = prm->src[0] + size_t(p) * prm->pair_stride[0];
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+                         " [%0], [%1], %2, [%3];"
+                         :: "r"(tiles), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+        }
+    }
+    __device__ __forceinline__ void tiles_wait() {
+        asm volatile("{\n\t.reg .pred P1;\n\t"
+                     "SPX_WAIT_%=:\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                     "@P1 bra SPX_DONE_%=;\n\t"
+                     "bra SPX_WAIT_%=;\n\t"
+                     "SPX_DONE_%=:\n\t}"
+                     :: "r"(mbar), "r"(parity) : "memory");
+    }
+    __device__ __forceinline__ void tiles_release() {
+        if (threadIdx.x == 0 && next_pair >= 0) tiles_issue(next_pair);
+    }
     __device__ __forceinline__ void cluster_sync() { cg::this_cluster().sync(); }
     __device__ __forceinline__ void global_fence() { __threadfence(); }
     __device__ __forceinline__ void or_status(int *p, int v) { atomicOr(p, v); }
@@ -318,8 +380,8 @@ __device__ __forceinline__ void prefetch_pair(const CcParams &prm, int k, const 
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams prm) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const __grid_constant__ CcParams prm) {
+    extern __shared__ __align__(128) unsigned char smem[];
     using L = Layout<C>;
     uint16_t *rrow = reinterpret_cast<uint16_t *>(smem + L::off_rrow);
     // one pair per CTA, or per cluster of CL CTAs
@@ -342,6 +404,18 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
 
     DevExec<C> ex;
     ex.red = reinterpret_cast<double *>(smem + L::off_red);
+    if (C::STAGE) {
+        ex.mbar = unsigned(__cvta_generic_to_shared(smem + L::off_mbar));
+        ex.tiles = unsigned(__cvta_generic_to_shared(smem + L::off_tiles));
+        ex.prm = &prm;
+        ex.parity = 0u;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(ex.mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (unit < prm.n) ex.tiles_issue(unit);              // the first pair of this CTA
+        }
+    }
 
     __shared__ int s_nrrow;
     if (threadIdx.x == 0) {
@@ -384,16 +458,27 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const CcParams pr
             }
             for (int s = 0; s < 5; ++s) job.base[s] = prm.src[s] + size_t(p) * prm.pair_stride[s];
         }
+        if (C::STAGE) {
+            // the tiles are (being) staged in shared memory: a full-size cutout at the origin
+            // of a NMAX x NMAX "image" (pixels outside the frame arrived as zeros)
+            const float *t0 = reinterpret_cast<const float *>(smem + L::off_tiles);
+            const int pitch = prm.boxes ? C::STAGE_PITCH : C::NMAX;
+            for (int s = 0; s < 5; ++s) job.base[s] = t0 + s * (C::NMAX * pitch);
+            job.x1 = prm.boxes ? (job.x1 & 3) : 0;          // the staged box starts at x1 & ~3
+            job.y1 = 0; job.pitch = pitch; job.H = C::NMAX; job.W = pitch;
+            ex.next_pair = k + nunits < prm.n ? k + nunits : -1;
+        }
         c.icc = prm.icc_out ? prm.icc_out + icc_off
                             : reinterpret_cast<float *>(slab + prm.off_icc);
         job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
-        if (rank == 0) prefetch_pair<C>(prm, k + nunits, pfmap);
+        if (rank == 0 && !C::STAGE) prefetch_pair<C>(prm, k + nunits, pfmap);
         // peak == NULL: packed [n,4] float64 result table (dx, dy, peak, status).  ONE call
         // site: a second inlined copy of process_pair costs 11 % (instruction cache)
         const bool packed = prm.peak == nullptr;
         process_pair<C>(c, ex, job, prm.shifts + (packed ? 4 : 2) * size_t(p),
                         packed ? nullptr : prm.peak + p, packed ? nullptr : prm.status + p);
+        if (C::STAGE) ex.parity ^= 1u;
     }
     if (C::CL > 1) cg::this_cluster().sync();      // do not exit while a peer may still read my W / R
 }
@@ -440,6 +525,77 @@ static int pick_cfg(int ny, int nx) {
     return 0;
 }
 
+// ---- TMA staging ------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// Can this launch use the TMA-staged form of its size class?  Uniform full-size cutouts only;
+// stack mode needs the five tiles of a pair contiguous and 16-byte aligned (one bulk copy),
+// frame mode a 16-byte aligned base and row pitch (tensor maps).  SPX_STAGE=1 opts in.
+// Descriptor slots in global memory: a small ring per device (allocated once), so that
+// launches on different streams do not share a slot while one of them is still running.
+static CUtensorMap *tmap_slot(cudaStream_t st, const CUtensorMap (&host)[5]) {
+    constexpr int kSlots = 64;
+    static CUtensorMap *ring[64] = {nullptr};
+    static unsigned next[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!ring[dev] && cudaMalloc(&ring[dev], kSlots * 5 * sizeof(CUtensorMap)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    CUtensorMap *slot = ring[dev] + 5 * (next[dev]++ % kSlots);
+    if (cudaMemcpyAsync(slot, host, 5 * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return slot;
+}
+
+static bool use_stage(CcParams &prm, int cfg, cudaStream_t st) {
+    static int want = -1;
+    if (want < 0) { const char *e = getenv("SPX_STAGE"); want = (e && atoi(e) != 0) ? 1 : 0; }
+    if (!want || (cfg != 32 && cfg != 64) || prm.shapes || prm.ny != cfg || prm.nx != cfg) return false;
+    const size_t tile = size_t(cfg) * cfg;
+    if (!prm.boxes) {
+        for (int s = 0; s < 5; ++s)
+            if (prm.src[s] != prm.src[0] + s * tile || prm.pair_stride[s] != prm.pair_stride[0]) return false;
+        return reinterpret_cast<uintptr_t>(prm.src[0]) % 16 == 0 && (prm.pair_stride[0] * 4) % 16 == 0;
+    }
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || (prm.pitch * 4) % 16 != 0) return false;
+    alignas(64) CUtensorMap host[5];
+    for (int s = 0; s < 5; ++s) {
+        if (reinterpret_cast<uintptr_t>(prm.src[s]) % 16 != 0) return false;
+        const cuuint64_t dims[2] = {cuuint64_t(prm.W), cuuint64_t(prm.H)};
+        const cuuint64_t strides[1] = {cuuint64_t(prm.pitch) * 4};
+        const cuuint32_t box[2] = {cuuint32_t(cfg + 4), cuuint32_t(cfg)}, estr[2] = {1, 1};
+        if (enc(&host[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(prm.src[s]), dims,
+                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    prm.tmap = tmap_slot(st, host);
+    return prm.tmap != nullptr;
+}
+
 static SlabPlan plan_for(int cfg, int ny, int nx, bool want_icc) {
     switch (cfg) {
         case 20: return plan_slab<Cfg20>(ny, nx, want_icc);
@@ -465,7 +621,11 @@ static int launch(CcParams &prm, const SlabPlan &sp, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(cc_fit_kernel<C>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
-    int grid = units_for(prm.n, sp) * C::CL;
+    // persistent grid of THIS configuration (a staged form runs fewer CTAs per SM than the
+    // plain form the workspace was sized for)
+    const long long cap = (long long)num_sms() * C::MINB / C::CL;
+    int grid = int(prm.n < cap ? prm.n : cap) * C::CL;
+    (void)sp;
     if (C::CL == 1) {
         cc_fit_kernel<C><<<grid, C::T, smem, stream>>>(prm);
     } else {
@@ -519,6 +679,8 @@ static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *
     prm.slab_bytes = sp.bytes;
     prm.off_icc = sp.off_icc; prm.off_w = sp.off_w; prm.off_r = sp.off_r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_stage(prm, cfg, st))
+        return cfg == 32 ? launch<Cfg32S>(prm, sp, st) : launch<Cfg64S>(prm, sp, st);
     switch (cfg) {
         case 20: return launch<Cfg20>(prm, sp, st);
         case 42: return launch<Cfg42>(prm, sp, st);

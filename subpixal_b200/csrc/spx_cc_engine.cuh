@@ -88,12 +88,26 @@ template <class C, bool INV = false> SPX_HD cf tw2(int n2, int k1) {
 // outputs of the k1 groups it does not own into their owners' shared memory) and IC2
 // (it loads them back) cross the cluster; the tile columns, and therefore all HBM
 // traffic, are split evenly.
+//
+// STAGE: the five tiles of a pair are staged in shared memory by the TMA (one bulk copy of
+// the contiguous [5][NMAX][NMAX] block of a stack, or five 2-D tensor copies out of the
+// frames whose out-of-bounds zero fill IS Cutout's 'fill' mode, cutout.py:737-752 - measured
+// on B200: rows / columns outside the tensor read as zeros, but a box whose first column is
+// not on a 16-byte boundary faults with "illegal instruction"), signalled
+// on an mbarrier; the copy for pair p+1 is issued as soon as the last C1 pass of pair p has
+// read its tiles, so the statistics and C1 passes read shared memory and never wait for HBM.
+// Only for full-size cutouts (ny = nx = NMAX); costs 20 NMAX^2 bytes of shared memory.
 template <int P_, int E1_, int E2_, int NMAX_, int T_, int MINB_, bool WSM_, bool RSM_,
-          bool INPLACE_ = false, int CL_ = 1>
+          bool INPLACE_ = false, int CL_ = 1, bool STAGE_ = false>
 struct CcCfg {
     static constexpr int P = P_, E1 = E1_, E2 = E2_, NMAX = NMAX_, T = T_, MINB = MINB_;
     static constexpr bool W_SMEM = WSM_, R_SMEM = RSM_, INPLACE = INPLACE_;
     static constexpr int CL = CL_;
+    static constexpr bool STAGE = STAGE_;
+    // (frame mode stages NMAX + 4 columns per row: the TMA wants the first column of a box
+    // on a 16-byte boundary, so the box starts at x1 & ~3 and the tile is read at x1 & 3)
+    static constexpr int STAGE_PITCH = NMAX_ + 4;
+    static constexpr size_t TILE_BYTES = STAGE_ ? size_t(20) * NMAX_ * STAGE_PITCH : 0;
     // the compile-time fast path for full-size interior cutouts places the tiles at
     // offset NMAX/2, which must be a multiple of E2 (see c1_pass)
     static constexpr bool HAS_FAST = (NMAX_ / 2) % E2_ == 0 && NMAX_ % CL_ == 0;
@@ -114,6 +128,7 @@ struct CcCfg {
     static constexpr size_t W_ELEMS = size_t(PL) * WP;
     static constexpr size_t S_ELEMS = INPLACE ? 0 : size_t(BATCH) * SP;
     static constexpr size_t R_ELEMS = size_t(RHL) * RP;
+    static_assert(!STAGE_ || (CL_ == 1 && WSM_ && (NMAX_ / 2) % E2_ == 0), "staged tiles: one CTA, fast path");
     static_assert(CL == 1 || ((CL == 2 || CL == 4 || CL == 8) && WSM_ && RSM_ && INPLACE_ &&
                               E1 % CL == 0 && P % CL == 0),
                   "cluster mode: W and R in shared memory, CL divides E1 and P");
@@ -180,7 +195,7 @@ struct Xchg {
 // what binds these kernels, the L2 has slack.  So the slab is the default and
 // -DSPX_KEEP_SURFACE=1 builds the on-chip form (tests/test_emulator.py keeps it alive).
 #if defined(SPX_KEEP_SURFACE) && SPX_KEEP_SURFACE
-template <class C> struct SurfaceInW { static constexpr bool value = C::W_SMEM && C::CL == 1; };
+template <class C> struct SurfaceInW { static constexpr bool value = C::W_SMEM && C::CL == 1 && !C::STAGE; };
 #else
 template <class C> struct SurfaceInW { static constexpr bool value = false; };
 #endif
@@ -268,6 +283,10 @@ SPX_HD int warp_of(int tid) {
 #endif
 }
 
+// tile loads of a configuration: staged tiles live in shared memory (plain loads), tiles in
+// global memory go through the read-only / streaming paths below
+template <class C> SPX_HD float ld_tile(const float *p);
+template <class C> SPX_HD float ld_tile_last(const float *p);
 SPX_HD float ld_f32(const float *p) {
 #if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
     return __ldg(p);
@@ -284,6 +303,9 @@ SPX_HD float ld_f32_last(const float *p) {
     return *p;
 #endif
 }
+
+template <class C> SPX_HD float ld_tile(const float *p) { return C::STAGE ? *p : ld_f32(p); }
+template <class C> SPX_HD float ld_tile_last(const float *p) { return C::STAGE ? *p : ld_f32_last(p); }
 
 // Row r = k1*E2 + k2 holds frequency ky = k1 + E1*k2 (in-place two-step order).
 // Cluster mode: CTA `rank` stores the groups k1 = 2j + rank at local rows j*E2 + k2.
@@ -399,7 +421,7 @@ SPX_HD StatPartial stats_thread(const Ctx<C> &c, int tid) {
             for (int u = 0; u < U; ++u) {                    // all loads first
                 const bool ok = y + u * C::NW < yhi;
 #pragma unroll
-                for (int s = 0; s < 5; ++s) v[u][s] = ok ? ld_f32(p[s] + u * step) : 0.f;
+                for (int s = 0; s < 5; ++s) v[u][s] = ok ? ld_tile<C>(p[s] + u * step) : 0.f;
             }
 #pragma unroll
             for (int s = 0; s < 5; ++s) p[s] += U * step;
@@ -526,21 +548,21 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             // generic path: the rows that exist depend on the item, so every row is a candidate
-            constexpr bool cand = !FAST || n1 == A0 || n1 == A1 || n1 == B0 || n1 == B1;
+            [[maybe_unused]] constexpr bool cand = !FAST || n1 == A0 || n1 == A1 || n1 == B0 || n1 == B1;
             if constexpr (FAST) {
                 if constexpr (n1 >= N1_LO && n1 < N1_HI) {
-                    va[n1] = ld_f32_last(pa0 + n1 * rs);
-                    if constexpr (IS_REF) vb[n1] = (cand && detect) ? ld_f32(pb0 + n1 * rs) : 0.f;
-                    else vb[n1] = ld_f32_last(pb0 + n1 * rs);
+                    va[n1] = ld_tile_last<C>(pa0 + n1 * rs);
+                    if constexpr (IS_REF) vb[n1] = (cand && detect) ? ld_tile<C>(pb0 + n1 * rs) : 0.f;
+                    else vb[n1] = ld_tile_last<C>(pb0 + n1 * rs);
                 } else {
                     va[n1] = 0.f; vb[n1] = 0.f;
                 }
             } else {
                 const int y = C::E2 * n1 + ybase;
                 const bool ok = y >= ylo && y < yhi;         // warp-uniform
-                va[n1] = (ok && ta.colok) ? ld_f32_last(pa0 + n1 * rs) : 0.f;
-                if constexpr (IS_REF) vb[n1] = (ok && tb.colok) ? ld_f32(pb0 + n1 * rs) : 0.f;
-                else vb[n1] = (ok && tb.colok) ? ld_f32_last(pb0 + n1 * rs) : 0.f;
+                va[n1] = (ok && ta.colok) ? ld_tile_last<C>(pa0 + n1 * rs) : 0.f;
+                if constexpr (IS_REF) vb[n1] = (ok && tb.colok) ? ld_tile<C>(pb0 + n1 * rs) : 0.f;
+                else vb[n1] = (ok && tb.colok) ? ld_tile_last<C>(pb0 + n1 * rs) : 0.f;
             }
         });
     };
@@ -635,7 +657,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
     // 16 loads per item on the fast path: two items fit the 64 px class's registers
     // (+1.6 %; the 32 and 128 px classes spill and lose 2-4 %)
 #if !defined(SPX_HOST_EMU) && !defined(SPX_NO_C1_PAIR)
-    constexpr bool kPairItems = FAST && C::NMAX == 64;
+    constexpr bool kPairItems = FAST && C::NMAX == 64 && !C::STAGE;   // (staged tiles: no L2 latency to hide)
 #else
     constexpr bool kPairItems = false;
 #endif
@@ -1219,6 +1241,9 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
     // (the detector keys of both CTAs are complete after this barrier; every thread
     // evaluates the same few comparisons, so the branch is uniform)
     if (lazy && IT < 2 && !lazy_decide(c.xl->det[c.dslot], b == 0)) return false;
+    // staged tiles: every thread is past its last tile read (the barrier that ended this C1
+    // pass) and the pair will not be restarted any more: the next pair's copy may overwrite them
+    if (C::STAGE && IT == 1) ex.tiles_release();
     ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
@@ -1328,7 +1353,9 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
 //                   after(lane) on the 32 lanes of the warp that merged it, barrier
 //   warp_fit(lane_f, final_f) one warp: sum lane_f(lane) over 32 lanes, then
 //                   final_f(sum) on one lane, then barrier
-//   cluster_sync()  barrier over both CTAs of a cluster (CL == 2 only)
+//   cluster_sync()  barrier over all CTAs of a cluster (CL > 1 only)
+//   tiles_wait()    (STAGE) block until the staged tiles of the current pair have landed
+//   tiles_release() (STAGE) the tiles were read for the last time: start staging the next pair
 //   global_fence()  make this thread block's global writes visible to the peer
 //   or_status(p,v)  atomic OR
 // The device executor is in spx_cc.cu; tools/host_emu.cu runs the same
@@ -1353,6 +1380,7 @@ SPX_HD void process_pair(Ctx<C> &c, Ex &ex, const PairJob &job,
 #pragma unroll 1
 #endif
     for (;;) {
+        if (C::STAGE) ex.tiles_wait();          // the TMA has landed this pair's tiles
         ex.parts(7, [&](int part) {
             if (part < 6) { fill_state(*ps, job, part); return; }
             // single CTA: nobody else touches the detector slot (cluster mode: see Xchg)

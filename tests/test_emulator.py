@@ -155,3 +155,22 @@ def test_surface_kept_in_shared_memory(emu):
                 dx, dy, ricc, _ = _oracle(stacks[k], name)
                 assert int(np.argmax(ricc)) == kept[1][k] and (kept[1][k] // (2 * n)) % 2 == 1
                 assert abs(kept[0][k, 0] - dx) < 5e-5 and abs(kept[0][k, 1] - dy) < 5e-5
+
+
+def test_staged_tile_forms_agree_with_the_plain_forms(emu):
+    """TMA-staged forms of the 32 / 64 px classes (tiles of the next pair are copied into
+    shared memory as soon as the last C1 pass of the current pair is over): bit-identical
+    to the plain forms for every cc_type, with and without a requested surface - a tile
+    overwritten too early (e.g. before a statistics-free attempt is abandoned and the pair
+    restarted) would show up here."""
+    for n in (32, 64):
+        stacks, _ = orc.random_pairs(4, n, n, seed=9 * n)
+        stacks[1, 1:] = 2.5                                    # constant phases: lazy attempt abandoned
+        stacks[2, 3, 4, 4] = np.nan
+        for t in range(3):
+            for no_icc in (0, 1):
+                plain = emu(stacks, t, no_icc=no_icc)
+                staged = emu(stacks, t, no_icc=no_icc, env={"SPX_EMU_STAGE": "1"})
+                assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(plain[:3], staged[:3])), (n, t)
+                if not no_icc:
+                    assert np.array_equal(plain[3], staged[3], equal_nan=True)

@@ -47,6 +47,11 @@ struct HostExec {
         for (int l = 0; l < 32; ++l) { FitSums f = lane_f(l); fit_add(tot, f); }
         final_f(tot);
     }
+    // staged tiles (C::STAGE): the TMA copy is emulated by a memcpy at the moment the kernel
+    // would issue it, so a tile that is overwritten too early shows up as a wrong result
+    const float *next_src = nullptr; float *tiles = nullptr; size_t tile_floats = 0;
+    void tiles_wait() {}
+    void tiles_release() { if (next_src) for (size_t i = 0; i < tile_floats; ++i) tiles[i] = next_src[i]; }
     pthread_barrier_t *bar = nullptr;          // cluster barrier (two host threads = two CTAs)
     void cluster_sync() { pthread_barrier_wait(bar); }
     void global_fence() {}
@@ -83,14 +88,23 @@ void run(int n, int ny, int nx, int cc_type, const float *stack, double *shifts,
             c[rk].Wall[o] = W[o].data(); c[rk].Rall[o] = R[o].data(); c[rk].xall[o] = &xc[o];
         }
     const size_t tile = size_t(ny) * nx;
+    std::vector<float> staged(C::STAGE ? 5 * tile : 1);
     auto body = [&](int rk) {
         HostExec<C> ex;
         ex.bar = &bar;
+        if (C::STAGE) {
+            ex.tiles = staged.data(); ex.tile_floats = 5 * tile;
+            ex.next_src = stack; ex.tiles_release();             // the first pair
+        }
         for (int p = 0; p < n; ++p) {
             c[rk].dslot = p & 1;
             c[rk].icc = icc + size_t(p) * 4 * tile;
             PairJob job;
             for (int s = 0; s < 5; ++s) job.base[s] = stack + (size_t(p) * 5 + s) * tile;
+            if (C::STAGE) {
+                for (int s = 0; s < 5; ++s) job.base[s] = staged.data() + s * tile;
+                ex.next_src = p + 1 < n ? stack + size_t(p + 1) * 5 * tile : nullptr;
+            }
             job.pitch = nx; job.H = ny; job.W = nx; job.x1 = 0; job.y1 = 0;
             job.ny = ny; job.nx = nx; job.cc_type = cc_type; job.status0 = 0;
             job.flags = 0; job.patch_icc = !g_no_icc;
@@ -124,11 +138,15 @@ int main(int argc, char **argv) {
     const int m = ny > nx ? ny : nx;
     // 170 / 256 px classes: 4- / 8-CTA cluster forms by default, SPX_EMU_SLAB=1: global-slab forms
     const bool slab = getenv("SPX_EMU_SLAB") && atoi(getenv("SPX_EMU_SLAB")) != 0;
+    // SPX_EMU_STAGE=1: the TMA-staged forms of the 32 / 64 px classes (full-size tiles only)
+    const bool stage = getenv("SPX_EMU_STAGE") && atoi(getenv("SPX_EMU_STAGE")) != 0;
     if (m <= 20) run<CcCfg<32, 4, 8, 20, 64, 12, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 32 && m <= 42) run<CcCfg<64, 8, 8, 42, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 64 && m <= 84) run<CcCfg<128, 8, 16, 84, 512, 1, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 128 && m <= 170 && slab) run<CcCfg<256, 16, 16, 170, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 128 && m <= 170) run<CcCfg<256, 16, 16, 170, 512, 1, true, true, true, 4>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m <= 32 && stage && ny == 32 && nx == 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true, 1, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m <= 64 && m > 42 && stage && ny == 64 && nx == 64) run<CcCfg<96, 12, 8, 64, 512, 1, true, true, true, 1, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, true, true, EMU128_INPLACE, 2>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());

@@ -726,10 +726,11 @@ SPX_HD bool lazy_decide(const unsigned (&det)[2], bool need_evidence) {
 }
 
 // C2: E2-point FFT over n2 for every (column, k1 group of mine), in place.
-template <class C>
+// (FAST: full-size tile - nx, ny and the surface width are compile-time constants)
+template <class C, bool FAST = false>
 SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = c.ps->nx;
+    const int nx = FAST ? C::NMAX : c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
     SPX_UNROLL_SMALL
     for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
@@ -749,10 +750,10 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
 }
 
 // IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
-template <class C>
+template <class C, bool FAST = false>
 SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = c.ps->nx;
+    const int nx = FAST ? C::NMAX : c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
     SPX_UNROLL_SMALL
     for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
@@ -800,13 +801,13 @@ SPX_HD void st_surface(float *p, float v0, float v1, bool scratch, unsigned long
 // n - yc of phases (a=0, b) [real part] and (a=1, b) [imaginary part].
 // Inputs were sanitised, so the surface is finite and a plain ">" scan in
 // increasing index order implements numpy's first-maximum rule per item.
-template <class C>
+template <class C, bool FAST = false>
 SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
-    const int ny = ps.ny, nx = local_cols(c, ps.nx);
+    const int ny = FAST ? C::NMAX : ps.ny, nx = FAST ? C::NXL : local_cols(c, ps.nx);
     const int nchunk = (nx + 31) >> 5;
-    const int w2 = 2 * ps.nx;
+    const int w2 = FAST ? 2 * C::NMAX : 2 * ps.nx;
     float *icc = c.icc;
     const bool keep = ps.keep != 0;              // nobody asked for the surface
     // (the 80-register classes have no room for the 64-bit policy across the item loop)
@@ -1007,10 +1008,10 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
 
 // X3: E1-point inverse FFT over k1; sample m = E2*n1+n2 is lag (m - shift) - xc,
 // kept (at position m of the row buffer) for 0 <= m - shift < nx.
-template <class C>
+template <class C, bool FAST = false>
 SPX_HD void x3_pass(const Ctx<C> &c, int tid, int cb, int ce, int shift) {
     const int warp = warp_of(tid), lane = tid & 31;
-    const int nx = c.ps->nx;
+    const int nx = FAST ? C::NMAX : c.ps->nx;
     SPX_UNROLL_BIG
     for (int wi = cb * C::E2 + warp; wi < ce * C::E2; wi += C::NW) {
         const int chunk = wi / C::E2, n2 = wi - chunk * C::E2;
@@ -1244,26 +1245,26 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
     // staged tiles: every thread is past its last tile read (the barrier that ended this C1
     // pass) and the pair will not be restarted any more: the next pair's copy may overwrite them
     if (C::STAGE && IT == 1) ex.tiles_release();
-    ex.par([&](int tid) { c2_pass<C>(c, tid, cin); });
+    ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, cin); });
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
         ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
-        ex.par([&](int tid) { x3_pass<C>(c, tid, 0, C::NCHUNK, xsh); });
+        ex.par([&](int tid) { x3_pass<C, FAST>(c, tid, 0, C::NCHUNK, xsh); });
     } else {
         for (int k = 0; k < C::NCHUNK; ++k) {
             if (!C::DIRECT) ex.par([&](int tid) { stage_in<C, false>(c, tid, k, xoff); });
             ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff); });
             ex.par([&](int tid) { x2_pass<C>(c, tid, k, k + 1); });
-            ex.par([&](int tid) { x3_pass<C>(c, tid, k, k + 1, xsh); });
+            ex.par([&](int tid) { x3_pass<C, FAST>(c, tid, k, k + 1, xsh); });
             if (!C::DIRECT) ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
         }
     }
-    ex.par([&](int tid) { ic1_pass<C>(c, tid, cout); });
+    ex.par([&](int tid) { ic1_pass<C, FAST>(c, tid, cout); });
     if (C::CL > 1) ex.cluster_sync();       // the peer's rows hold their lags: IC2 may read them
     // W now holds this pair's surface (keep).  After the first pair the warp that finishes
     // the argmax also saves the window around the best sample of that pair, before the
     // barrier that lets the next C1 pass overwrite W.
-    ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C>(c, tid, b, ysh, cout); },
+    ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C, FAST>(c, tid, b, ysh, cout); },
                         [&](int lane) {
         if (!keep) return;
         if (lane == 0) { ps->in_w = b; ps->ysh = ysh; ps->cout = cout; }
@@ -1286,7 +1287,9 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
     // placement offset of the image tiles and the resulting index shift of the
     // wanted lags: sample m of the circular correlation is lag (m - off)
     const int yoff = FAST ? C::NMAX / 2 : ps->yc, xoff = FAST ? C::NMAX / 2 : ps->xc;
-    const int ysh = yoff - ps->yc, xsh = xoff - ps->xc;
+    // (compile-time in both cases: the generic path places the tiles at (yc, xc) itself)
+    constexpr int kSh = FAST ? C::NMAX / 2 - (C::NMAX - 1) / 2 : 0;
+    const int ysh = kSh, xsh = kSh;
     // INPLACE: W columns are padded positions (input column i sits at i + xoff,
     // wanted lag sample l at l + xsh)
     const int cin = C::INPLACE ? xoff : 0, cout = C::INPLACE ? xsh : 0;
@@ -1301,7 +1304,7 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
         if (fl) ex.or_status(&ps->status, fl);
     });
     if (C::CL > 1) ex.cluster_sync();           // the peer's half of my rows has arrived
-    ex.par([&](int tid) { c2_pass<C>(c, tid, 0); });
+    ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, 0); });
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, 0, C::RCHUNK, 0); });
         ex.par([&](int tid) { x2_ref_pass<C>(c, tid, 0, C::RCHUNK); });

@@ -375,6 +375,19 @@ SPX_HD void stat_merge(StatPartial &a, const StatPartial &b) {
     a.rcnt += b.rcnt; a.rsum += b.rsum; a.rsq += b.rsq; a.flags |= b.flags;
 }
 
+// max(acc, |v|) that PROPAGATES NaN (one FMNMX.NAN with an |.| operand): the running
+// "largest magnitude" of a batch of pixels is NaN / Inf iff one of them is
+SPX_HD float absmax_nan(float acc, float v) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(acc), "f"(fabsf(v)));
+    return r;
+#else
+    const float a = fabsf(v);
+    return (acc != acc || a != a) ? NAN : (a > acc ? a : acc);
+#endif
+}
+
 // non-finite pixels become 0; they raise the tile's status bit unless the
 // caller asked for masked-pixel zeroing (align.py:661)
 // internal status bit: a non-finite pixel was seen (reported or silently zeroed);
@@ -425,14 +438,12 @@ SPX_HD StatPartial stats_thread(const Ctx<C> &c, int tid) {
             }
 #pragma unroll
             for (int s = 0; s < 5; ++s) p[s] += U * step;
-            unsigned worst = 0u;
+            float wacc = 0.f;
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int s = 0; s < 5; ++s) {
-                    const unsigned b = f32_bits(v[u][s]) & 0x7fffffffu;
-                    worst = worst > b ? worst : b;
-                }
+                for (int s = 0; s < 5; ++s) wacc = absmax_nan(wacc, v[u][s]);
+            const unsigned worst = f32_bits(wacc) & 0x7fffffffu;
             if (worst >= 0x7f800000u) {                      // rare: NaN / Inf present
 #pragma unroll
                 for (int u = 0; u < U; ++u)
@@ -570,26 +581,27 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
         const int n2 = wi % C::E2, i = (wi / C::E2) * 32 + lane;
         const bool active = FAST || i < nx;
         const int ybase = n2 - yoff;
-        // one cheap test for "any NaN/Inf among my pixels": max of |bits|
+        // one cheap test for "any NaN/Inf among my pixels": NaN-propagating max of |pixel|
         unsigned worst = 0u;
         if constexpr (CHECK) {
+            float wacc = 0.f;
             static_for<N1_LO, N1_HI>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
-                const unsigned ua = f32_bits(va[n1]) & 0x7fffffffu, ub = f32_bits(vb[n1]) & 0x7fffffffu;
-                worst = worst > ua ? worst : ua;
-                if (pair) worst = worst > ub ? worst : ub;
+                wacc = absmax_nan(wacc, va[n1]);
+                if (pair) wacc = absmax_nan(wacc, vb[n1]);
             });
+            worst = f32_bits(wacc) & 0x7fffffffu;
         }
         if (CHECK && worst >= 0x7f800000u) {                 // rare
-            worst = 0u;
+            float wacc = 0.f;
             static_for<0, C::E1>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
                 va[n1] = sanitize(va[n1], sa, report, flags);
                 if (pair) vb[n1] = sanitize(vb[n1], sb, report, flags);
-                const unsigned ua = f32_bits(va[n1]) & 0x7fffffffu, ub = f32_bits(vb[n1]) & 0x7fffffffu;
-                worst = worst > ua ? worst : ua;
-                if (pair) worst = worst > ub ? worst : ub;
+                wacc = absmax_nan(wacc, va[n1]);
+                if (pair) wacc = absmax_nan(wacc, vb[n1]);
             });
+            worst = f32_bits(wacc) & 0x7fffffffu;
         }
         if constexpr (CHECK) amax = amax > worst ? amax : worst;
         if (!FAST && detect) {

@@ -37,6 +37,10 @@ struct CcParams {
     // staged configurations, frame mode: one 2-D tensor map per frame (box NMAX x NMAX,
     // out-of-bounds elements read as zero = Cutout 'fill' mode), in global memory
     const CUtensorMap *tmap;
+    // dynamic work distribution (single-CTA classes): pairs beyond the first two of a CTA
+    // are claimed from this counter (zeroed before the launch), so that a CTA that starts
+    // late - e.g. because an NCCL kernel still occupies its SM - simply takes fewer pairs
+    unsigned *claim;
 };
 
 // ---- configurations (one per supported maximum cutout size) -----------------
@@ -429,7 +433,15 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const __grid_cons
     const size_t icc_elems = size_t(4) * prm.ny * prm.nx;
     const PfMap pfmap = prefetch_map(prm.nx, threadIdx.x & 31);
     c.dslot = 0;
-    for (int k = unit; k < prm.n; k += nunits, c.dslot ^= 1) {
+    // Pair k of iteration i: the first two are static (unit, unit + nunits); with a claim
+    // counter thread 0 claims the pair of iteration i + 2 at the start of iteration i and
+    // parks it in s_claim[i & 1], which everybody reads after the barriers of the pair.
+    __shared__ int s_claim[2];
+    const bool dynamic = C::CL == 1 && !C::STAGE && prm.claim != nullptr;
+    int knext = unit + nunits;
+    for (int k = unit, it = 0; k < prm.n; ++it, c.dslot ^= 1) {
+        if (dynamic && threadIdx.x == 0)
+            s_claim[it & 1] = 2 * nunits + int(atomicAdd(prm.claim, 1u));
         const int p = prm.order ? __ldg(prm.order + k) : k;
         PairJob job;
         job.x1 = 0; job.y1 = 0; job.status0 = 0;
@@ -466,19 +478,21 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const __grid_cons
             for (int s = 0; s < 5; ++s) job.base[s] = t0 + s * (C::NMAX * pitch);
             job.x1 = prm.boxes ? (job.x1 & 3) : 0;          // the staged box starts at x1 & ~3
             job.y1 = 0; job.pitch = pitch; job.H = C::NMAX; job.W = pitch;
-            ex.next_pair = k + nunits < prm.n ? k + nunits : -1;
+            ex.next_pair = knext < prm.n ? knext : -1;
         }
         c.icc = prm.icc_out ? prm.icc_out + icc_off
                             : reinterpret_cast<float *>(slab + prm.off_icc);
         job.cc_type = prm.cc_type;
         job.flags = prm.flags; job.patch_icc = prm.icc_out != nullptr;
-        if (rank == 0 && !C::STAGE) prefetch_pair<C>(prm, k + nunits, pfmap);
+        if (rank == 0 && !C::STAGE) prefetch_pair<C>(prm, knext, pfmap);
         // peak == NULL: packed [n,4] float64 result table (dx, dy, peak, status).  ONE call
         // site: a second inlined copy of process_pair costs 11 % (instruction cache)
         const bool packed = prm.peak == nullptr;
         process_pair<C>(c, ex, job, prm.shifts + (packed ? 4 : 2) * size_t(p),
                         packed ? nullptr : prm.peak + p, packed ? nullptr : prm.status + p);
         if (C::STAGE) ex.parity ^= 1u;
+        k = knext;
+        knext = dynamic ? s_claim[it & 1] : knext + nunits;
     }
     if (C::CL > 1) cg::this_cluster().sync();      // do not exit while a peer may still read my W / R
 }
@@ -596,6 +610,24 @@ static bool use_stage(CcParams &prm, int cfg, cudaStream_t st) {
     return prm.tmap != nullptr;
 }
 
+// Claim counters of the dynamic work distribution: a ring of device words (no allocation);
+// every launch takes the next one and zeroes it in stream order.
+__device__ unsigned g_claim_ring[256];
+static unsigned *claim_slot(cudaStream_t st) {
+    static unsigned *base[64] = {nullptr};
+    static unsigned next[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!base[dev]) {
+        void *p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_claim_ring) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        base[dev] = static_cast<unsigned *>(p);
+    }
+    unsigned *slot = base[dev] + (next[dev]++ % 256);
+    if (cudaMemsetAsync(slot, 0, sizeof(unsigned), st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return slot;
+}
+
 static SlabPlan plan_for(int cfg, int ny, int nx, bool want_icc) {
     switch (cfg) {
         case 20: return plan_slab<Cfg20>(ny, nx, want_icc);
@@ -679,6 +711,9 @@ static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *
     prm.slab_bytes = sp.bytes;
     prm.off_icc = sp.off_icc; prm.off_w = sp.off_w; prm.off_r = sp.off_r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static int want_dynamic = -1;       // SPX_STATIC=1: static round-robin assignment (A/B knob)
+    if (want_dynamic < 0) { const char *e = getenv("SPX_STATIC"); want_dynamic = (e && atoi(e) != 0) ? 0 : 1; }
+    prm.claim = want_dynamic ? claim_slot(st) : nullptr;     // (cluster classes ignore it)
     if (use_stage(prm, cfg, st))
         return cfg == 32 ? launch<Cfg32S>(prm, sp, st) : launch<Cfg64S>(prm, sp, st);
     switch (cfg) {

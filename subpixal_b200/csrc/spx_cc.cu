@@ -157,7 +157,7 @@ template <class C> struct Layout {
     // [NW][8] doubles (statistics); the argmax reduction keeps its indices at byte 256
     static constexpr size_t red_bytes = C::NW * 64 > 512 ? C::NW * 64 : 512;
     static constexpr size_t off_xchg = off_red + red_bytes;       // Xchg (whole only in cluster mode)
-    static constexpr size_t xchg_bytes = C::CL > 1 ? 640 : 64;
+    static constexpr size_t xchg_bytes = C::CL > 1 ? 656 : 64;
     static constexpr size_t off_win = off_xchg + xchg_bytes;      // FitWin (surface kept in W)
     static constexpr size_t win_bytes = SurfaceInW<C>::value ? 832 : 0;
     static constexpr size_t off_rrow = off_win + win_bytes;
@@ -172,7 +172,7 @@ template <class C> struct Layout {
     static constexpr size_t off_mbar = off_tiles + C::TILE_BYTES;
     static constexpr size_t total = C::STAGE ? off_mbar + 16 : off_R + (C::R_SMEM ? C::R_ELEMS * 8 : 0);
     static_assert(sizeof(PairState) <= 256, "PairState must fit its slot");
-    static_assert(sizeof(Xchg) <= 640 && offsetof(Xchg, stat) <= 64, "Xchg must fit its slot");
+    static_assert(sizeof(Xchg) <= 656 && offsetof(Xchg, stat) <= 64, "Xchg must fit its slot");
     static_assert(sizeof(FitWin) <= 832, "FitWin must fit its slot");
 };
 
@@ -437,11 +437,16 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const __grid_cons
     // counter thread 0 claims the pair of iteration i + 2 at the start of iteration i and
     // parks it in s_claim[i & 1], which everybody reads after the barriers of the pair.
     __shared__ int s_claim[2];
-    const bool dynamic = C::CL == 1 && !C::STAGE && prm.claim != nullptr;
+    // (cluster classes: rank 0 claims for the cluster and writes the pair into every CTA's
+    // exchange block; the cluster barriers of the pair order the write before the reads)
+    const bool dynamic = !C::STAGE && prm.claim != nullptr;
     int knext = unit + nunits;
     for (int k = unit, it = 0; k < prm.n; ++it, c.dslot ^= 1) {
-        if (dynamic && threadIdx.x == 0)
-            s_claim[it & 1] = 2 * nunits + int(atomicAdd(prm.claim, 1u));
+        if (dynamic && threadIdx.x == 0 && rank == 0) {
+            const int v = 2 * nunits + int(atomicAdd(prm.claim, 1u));
+            if (C::CL == 1) s_claim[it & 1] = v;
+            else for (int r = 0; r < C::CL; ++r) X_of<C>(c, r)->claim[it & 1] = v;
+        }
         const int p = prm.order ? __ldg(prm.order + k) : k;
         PairJob job;
         job.x1 = 0; job.y1 = 0; job.status0 = 0;
@@ -492,7 +497,7 @@ __global__ void __launch_bounds__(C::T, C::MINB) cc_fit_kernel(const __grid_cons
                         packed ? nullptr : prm.peak + p, packed ? nullptr : prm.status + p);
         if (C::STAGE) ex.parity ^= 1u;
         k = knext;
-        knext = dynamic ? s_claim[it & 1] : knext + nunits;
+        knext = !dynamic ? knext + nunits : (C::CL == 1 ? s_claim[it & 1] : c.xl->claim[it & 1]);
     }
     if (C::CL > 1) cg::this_cluster().sync();      // do not exit while a peer may still read my W / R
 }

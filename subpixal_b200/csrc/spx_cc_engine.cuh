@@ -172,6 +172,7 @@ struct Xchg {
     // the current pair - the only window in which the peer can neither still read it
     // (previous pair) nor already write it (next pair).
     unsigned det[2][2];
+    int claim[2];          // cluster mode: the pair rank 0 claimed for iteration i + 2 (slot i & 1)
     double stat[kMaxCluster][8];
     float bestv[kMaxCluster];
     int besti[kMaxCluster];

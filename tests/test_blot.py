@@ -348,3 +348,41 @@ def test_gpu_blot_matches_the_frozen_oracle_outputs():
         for k in range(4):
             want = g["%s%d" % (interp, k)]
             assert np.array_equal(out[o[k]:o[k + 1]].reshape(want.shape).view(np.uint32), want.view(np.uint32))
+
+
+def test_everett_form_equals_six_point_lagrange():
+    """A structurally independent witness for the interpolator's algebra (the blot row
+    stays PARITY UNPINNED - drizzlepac is absent - but the Everett central-difference
+    form the oracle and the kernel share must at least be THE quintic through the six
+    samples): compare it with the float64 Lagrange polynomial through the same six
+    points, in 1-D and as the 6x6 tensor product of `interp_poly5`."""
+    from oracle import blot_oracle as bo
+    rng = np.random.default_rng(12)
+
+    def lagrange6(f, s):                      # nodes -2..3, evaluated at s, float64
+        nodes = np.arange(-2, 4, dtype=np.float64)
+        out = 0.0
+        for k in range(6):
+            w = 1.0
+            for m in range(6):
+                if m != k:
+                    w *= (s - nodes[m]) / (nodes[k] - nodes[m])
+            out += w * float(f[k])
+        return out
+
+    for _ in range(200):
+        f = rng.standard_normal(6).astype(np.float32) * 10
+        s = np.float32(rng.uniform(0, 1))
+        got = float(bo._everett(*f, s))
+        want = lagrange6(f.astype(np.float64), float(s))
+        assert abs(got - want) < 1e-5 * max(1.0, np.abs(f).max())
+    # 2-D: interior points of a random image (no edge extension involved)
+    img = rng.standard_normal((24, 24)).astype(np.float32)
+    for _ in range(100):
+        x, y = rng.uniform(4, 18, 2)
+        got = float(bo.interp_poly5(img, np.float32(x), np.float32(y)))
+        ix, iy = int(x), int(y)
+        sx, sy = float(np.float32(x)) - ix, float(np.float32(y)) - iy
+        rows = [lagrange6(img[iy + dj, ix - 2:ix + 4].astype(np.float64), sx) for dj in range(-2, 4)]
+        want = lagrange6(np.array(rows), sy)
+        assert abs(got - want) < 2e-5 * max(1.0, float(np.abs(img).max()))

@@ -273,6 +273,37 @@ typedef struct spx_blot_args {
 size_t spx_blot_workspace_bytes(int src_h, int src_w);
 int spx_blot_phases(const spx_blot_args *args_host, void *stream);
 
+/* ========================================================================
+ * (7) FITS image payload -> native device array (section 8f rank 4: ingest).
+ * Replaces what astropy.io.fits does when align.py reads `h[ext].data`
+ * (align.py:311-320, 466-486) and catalogs.py:757 `fits.getdata`: big-endian
+ * two's-complement / IEEE-754 elements (FITS standard 4.0, sections 5.2, 5.3)
+ * to native order, the BSCALE / BZERO linear scaling (section 4.4.2.5), and -
+ * fused into the same sweep - the two per-pixel operations align.py applies
+ * right after reading: `img_sci -= sky` (align.py:480-481) and
+ * `np.equal(wht, 0.0)` (align.py:312, the "DQ" of a drizzled weight image).
+ * HBM-bound byte work: every element is read once and written once.
+ *
+ * raw        the HDU's data block as it is in the file (uploaded by the caller),
+ *            16-byte aligned; n elements of |bitpix| / 8 bytes.
+ * bitpix     8 (unsigned bytes), 16, 32, 64 (signed), -32, -64 (IEEE).
+ * out_kind   SPX_T_F32 / SPX_T_F64: out = T(raw) [* T(bscale)] [+ T(bzero)] [- T(sky)],
+ *            each step rounded once in T (no contraction), a step is skipped when
+ *            its constant is the identity - numpy's in-place `*=`, `+=`, `-=` on an
+ *            array of dtype T, which is how astropy scales (float32 for BITPIX 8 / 16,
+ *            float64 for 32 / 64);
+ *            SPX_T_I8..I64 of the SAME width as the input (bitpix > 0): integer
+ *            payload, bscale must be 1, sky 0, and out = raw + bzero modulo 2^width
+ *            (bzero = 2^(width-1) is the FITS convention for unsigned integers:
+ *            the stored bits are then the unsigned value).
+ * out        16-byte aligned; may alias `raw` when the element widths agree.
+ * zero_mask  optional, 16-byte aligned, element type mask_kind (SPX_T_I8 / I32 / I64):
+ *            1 where the DECODED value (before the sky subtraction) equals 0.
+ * ======================================================================== */
+int spx_fits_decode(const void *raw, int64_t n, int bitpix, double bscale, double bzero,
+                    double sky, int out_kind, void *out, int mask_kind, void *zero_mask,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ EXPORTS = ("spx_abi_version", "spx_error_string", "spx_gather_cutouts",
            "spx_cc_workspace_bytes", "spx_cc_fit_stack", "spx_cc_fit_ragged",
            "spx_cc_fit_frames",
            "spx_find_peak", "spx_segment_boxes", "spx_blot_phases",
-           "spx_blot_workspace_bytes")
+           "spx_blot_workspace_bytes", "spx_fits_decode")
 BLOT_NEAREST, BLOT_LINEAR, BLOT_POLY5, BLOT_POLY3 = 0, 1, 2, 3
 BLOT_MAX_PHASES = 8
 
@@ -111,6 +111,9 @@ def load():
     lib.spx_blot_workspace_bytes.argtypes = [i32, i32]
     lib.spx_blot_phases.restype = i32
     lib.spx_blot_phases.argtypes = [C.POINTER(BlotArgs), vp]
+    lib.spx_fits_decode.restype = i32
+    lib.spx_fits_decode.argtypes = [vp, i64, i32, C.c_double, C.c_double, C.c_double,
+                                    i32, vp, i32, vp, vp]
     if lib.spx_abi_version() != ABI_VERSION:
         raise RuntimeError("subpixal_b200: ABI version mismatch, rebuild the library")
     _lib = lib

@@ -14,7 +14,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_native")
 LIB_PATH = os.path.join(OUT_DIR, "libsubpixal_b200.so")
-SOURCES = ("spx_api.cu", "spx_gather.cu", "spx_peak.cu", "spx_segbox.cu", "spx_blot.cu", "spx_cc.cu")
+SOURCES = ("spx_api.cu", "spx_gather.cu", "spx_peak.cu", "spx_segbox.cu", "spx_blot.cu", "spx_ingest.cu",
+           "spx_cc.cu")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

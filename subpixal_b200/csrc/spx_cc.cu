@@ -97,12 +97,15 @@ using Cfg84  = CcCfg<128,  8, 16,  84, SPX84_T, 1, true,  true,  true>;
 #define SPX170_CLUSTER 0
 #endif
 #ifndef SPX170_T
-#define SPX170_T 512
+#define SPX170_T (SPX170_CLUSTER ? 512 : 256)
 #endif
 #if SPX170_CLUSTER
 using Cfg170 = CcCfg<256, 16, 16, 170, SPX170_T, 1, true, true, true, 4>;  // 4-CTA cluster, DSMEM
 #else
-using Cfg170 = CcCfg<256, 16, 16, 170, 512, 1, false, false>;              // W / R in a global slab
+#ifndef SPX170_MINB
+#define SPX170_MINB 2
+#endif
+using Cfg170 = CcCfg<256, 16, 16, 170, SPX170_T, SPX170_MINB, false, false>;   // W / R in a global slab
 #endif
 using Cfg32  = CcCfg< 48, SPX32_E1, 48 / SPX32_E1,  32, SPX32_T, SPX32_MINB, true,  true,  true>;
 using Cfg64  = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64_T, SPX64_MINB, true,  true,  true>;
@@ -141,11 +144,14 @@ using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
 #endif
 using Cfg256 = CcCfg<384, 24, 16, 256, SPX256_T, 1, true, true, true, 8>;  // 8-CTA cluster, DSMEM
 #else
+// (two CTAs of 8 warps per SM: with the fused column passes the only shared memory is the
+// 98.6 KB scratch S, and two CTAs hide each other's copy passes - 210 k vs 191 k pairs/s for
+// one CTA of 16 warps, 180 k for the unfused form)
 #ifndef SPX256_T
-#define SPX256_T 512
+#define SPX256_T 256
 #endif
 #ifndef SPX256_MINB
-#define SPX256_MINB 1
+#define SPX256_MINB 2
 #endif
 using Cfg256 = CcCfg<384, 24, 16, 256, SPX256_T, SPX256_MINB, false, false>;   // W / R in a global slab
 #endif
@@ -719,6 +725,15 @@ static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *
     static int want_dynamic = -1;       // SPX_STATIC=1: static round-robin assignment (A/B knob)
     if (want_dynamic < 0) { const char *e = getenv("SPX_STATIC"); want_dynamic = (e && atoi(e) != 0) ? 0 : 1; }
     prm.claim = want_dynamic ? claim_slot(st) : nullptr;     // (cluster classes ignore it)
+#ifdef SPX_ONLY          // developer knob: compile ONE size class (fast ptxas / SASS turn-around)
+#define SPX_CASE(N, CFG) case N: if (SPX_ONLY == N) return launch<CFG>(prm, sp, st); return SPX_E_UNSUPPORTED;
+    switch (cfg) {
+        SPX_CASE(20, Cfg20) SPX_CASE(42, Cfg42) SPX_CASE(84, Cfg84) SPX_CASE(170, Cfg170)
+        SPX_CASE(32, Cfg32) SPX_CASE(64, Cfg64) SPX_CASE(128, Cfg128) SPX_CASE(256, Cfg256)
+        default: return SPX_E_UNSUPPORTED;
+    }
+#undef SPX_CASE
+#else
     if (use_stage(prm, cfg, st))
         return cfg == 32 ? launch<Cfg32S>(prm, sp, st) : launch<Cfg64S>(prm, sp, st);
     switch (cfg) {
@@ -731,6 +746,7 @@ static int run_cc(CcParams &prm, void *workspace, size_t workspace_bytes, void *
         case 128: return launch<Cfg128>(prm, sp, st);
         default: return launch<Cfg256>(prm, sp, st);
     }
+#endif
 }
 
 }  // namespace spx

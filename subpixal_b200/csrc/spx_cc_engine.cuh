@@ -46,6 +46,11 @@
 #else
 #define SPX_UNROLL_BIG
 #endif
+#if !defined(SPX_HOST_EMU)
+#define SPX_NO_UNROLL _Pragma("unroll 1")
+#else
+#define SPX_NO_UNROLL
+#endif
 
 namespace spx {
 
@@ -119,6 +124,16 @@ struct CcCfg {
     // how the row stage reaches its rows: in place in W / directly in W (shared
     // memory, lanes along rows) / staged through S by coalesced copies (W global)
     static constexpr bool DIRECT = !INPLACE && WSM_;
+    // W in global memory (slab classes): the two column passes on either side of the row
+    // stage are FUSED per 32-column chunk through the scratch S (C1 -> C2 -> copy out;
+    // copy in -> IC1 -> IC2), so W makes one trip to the slab per direction change instead
+    // of three (see phase_pair)
+#ifndef SPX_NO_FUSE
+    static constexpr bool FUSE = !WSM_ && !INPLACE_ && CL_ == 1;
+#else
+    static constexpr bool FUSE = false;
+#endif
+    static constexpr int CP = 32;            // pitch of a column chunk held in S: [PL][32]
     static constexpr int SP = P + 1;         // pitch of the row scratch, odd
     static constexpr int RP = P + 1;         // pitch of R, odd
     static constexpr int RH = P / 2 + 1;     // rows of R (half spectrum)
@@ -521,9 +536,10 @@ SPX_HD bool lazy_evidence(float u, float w) {
     const float m = fmaxf(fabsf(u), fabsf(w));
     return fabsf(u - w) >= 1e-3f * m && m >= 1e-12f;
 }
-template <class C, bool FAST, bool IS_REF, bool CHECK = true>
+// CHUNK: only the items of 32-column chunk `chunk`, written to S as [PL][CP] (column = lane)
+template <class C, bool FAST, bool IS_REF, bool CHECK = true, bool CHUNK = false>
 SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
-                   int lazy = 0) {
+                   int lazy = 0, int chunk = 0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NXL : local_cols(c, ps.nx), ny = FAST ? C::NMAX : ps.ny;
@@ -657,7 +673,12 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
             });
         }
         RegFFT<C::E1, false>::run(x);
-        if (active) {
+        if (CHUNK) {                                         // (idle lanes write zeros)
+            static_for<0, C::E1>([&](auto K1) {
+                constexpr int k1 = decltype(K1)::value;
+                c.S[(k1 * C::E2 + n2) * C::CP + lane] = cmul(x[k1], tw2<C>(n2, k1));
+            });
+        } else if (active) {
             const int gi = c.col_lo + i + col0;              // column inside W
             static_for<0, C::E1>([&](auto K1) {
                 constexpr int k1 = decltype(K1)::value;
@@ -666,7 +687,8 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
             });
         }
     };
-    const int nitems = nchunk * C::E2;
+    const int nitems = CHUNK ? (chunk + 1) * C::E2 : nchunk * C::E2;
+    const int item0 = CHUNK ? chunk * C::E2 : 0;
     // 16 loads per item on the fast path: two items fit the 64 px class's registers
     // (+1.6 %; the 32 and 128 px classes spill and lose 2-4 %)
 #if !defined(SPX_HOST_EMU) && !defined(SPX_NO_C1_PAIR)
@@ -677,7 +699,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
     if constexpr (kPairItems) {
         // two items per iteration: the tile loads of the second (L2 latency) are in flight
         // while the first goes through its FFT
-        for (int wi = warp; wi < nitems; wi += 2 * C::NW) {
+        for (int wi = item0 + warp; wi < nitems; wi += 2 * C::NW) {
             float va0[C::E1], vb0[C::E1], va1[C::E1], vb1[C::E1];
             const bool two = wi + C::NW < nitems;            // warp-uniform
             load_item(wi, va0, vb0);
@@ -687,7 +709,7 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
         }
     } else {
         SPX_UNROLL_BIG
-        for (int wi = warp; wi < nitems; wi += C::NW) {
+        for (int wi = item0 + warp; wi < nitems; wi += C::NW) {
             float va[C::E1], vb[C::E1];
             load_item(wi, va, vb);                           // all loads first (independent)
             finish_item(wi, va, vb);                         // arithmetic afterwards
@@ -740,48 +762,56 @@ SPX_HD bool lazy_decide(const unsigned (&det)[2], bool need_evidence) {
 
 // C2: E2-point FFT over n2 for every (column, k1 group of mine), in place.
 // (FAST: full-size tile - nx, ny and the surface width are compile-time constants)
-template <class C, bool FAST = false>
-SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0) {
+template <class C, bool FAST = false, bool CHUNK = false>
+SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
+    constexpr int WPc = CHUNK ? C::CP : C::WP;
+    cf *wbase = CHUNK ? c.S : c.W;
+    const int item0 = CHUNK ? chunk * C::E1L : 0, item1 = CHUNK ? (chunk + 1) * C::E1L : nchunk * C::E1L;
     SPX_UNROLL_SMALL
-    for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
+    for (int wi = item0 + warp; wi < item1; wi += C::NW) {
         const int j = wi % C::E1L, i = (wi / C::E1L) * 32 + lane;
         if (i >= nx) continue;
+        const int col = CHUNK ? lane : i + col0;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            x[n2] = c.W[(j * C::E2 + n2) * C::WP + i + col0];
+            x[n2] = wbase[(j * C::E2 + n2) * WPc + col];
         });
         RegFFT<C::E2, false>::run(x);
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            c.W[(j * C::E2 + k2) * C::WP + i + col0] = x[k2];
+            wbase[(j * C::E2 + k2) * WPc + col] = x[k2];
         });
     }
 }
 
 // IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
-template <class C, bool FAST = false>
-SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0) {
+template <class C, bool FAST = false, bool CHUNK = false>
+SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
+    constexpr int WPc = CHUNK ? C::CP : C::WP;
+    cf *wbase = CHUNK ? c.S : c.W;
+    const int item0 = CHUNK ? chunk * C::E1L : 0, item1 = CHUNK ? (chunk + 1) * C::E1L : nchunk * C::E1L;
     SPX_UNROLL_SMALL
-    for (int wi = warp; wi < nchunk * C::E1L; wi += C::NW) {
+    for (int wi = item0 + warp; wi < item1; wi += C::NW) {
         const int j = wi % C::E1L, l = (wi / C::E1L) * 32 + lane;
         const int k1 = j * C::CL + c.rank;
         if (l >= nx) continue;
+        const int col = CHUNK ? lane : l + col0;
         cf x[C::E2];
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            x[k2] = c.W[(j * C::E2 + k2) * C::WP + l + col0];
+            x[k2] = wbase[(j * C::E2 + k2) * WPc + col];
         });
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
-            c.W[(j * C::E2 + n2) * C::WP + l + col0] = cmul(x[n2], tw2<C, true>(n2, k1));
+            wbase[(j * C::E2 + n2) * WPc + col] = cmul(x[n2], tw2<C, true>(n2, k1));
         });
     }
 }
@@ -814,8 +844,8 @@ SPX_HD void st_surface(float *p, float v0, float v1, bool scratch, unsigned long
 // n - yc of phases (a=0, b) [real part] and (a=1, b) [imaginary part].
 // Inputs were sanitised, so the surface is finite and a plain ">" scan in
 // increasing index order implements numpy's first-maximum rule per item.
-template <class C, bool FAST = false>
-SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
+template <class C, bool FAST = false, bool CHUNK = false>
+SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0, int chunk = 0) {
     const PairState &ps = *c.ps;
     const int warp = warp_of(tid), lane = tid & 31;
     const int ny = FAST ? C::NMAX : ps.ny, nx = FAST ? C::NXL : local_cols(c, ps.nx);
@@ -828,16 +858,21 @@ SPX_HD Best ic2_pass(const Ctx<C> &c, int tid, int b, int shift, int col0) {
     const int cbase = 2 * c.col_lo;              // my columns start at surface column 2*col_lo
     const WBases<C> wr = w_bases<C>(c);
     Best best = best_init();
+    const int item0 = CHUNK ? chunk * C::E2 : 0, item1 = CHUNK ? (chunk + 1) * C::E2 : nchunk * C::E2;
     SPX_UNROLL_BIG
-    for (int wi = warp; wi < nchunk * C::E2; wi += C::NW) {
+    for (int wi = item0 + warp; wi < item1; wi += C::NW) {
         const int n2 = wi % C::E2, l = (wi / C::E2) * 32 + lane;
         if (l >= nx) continue;
         cf x[C::E1];
         const int gl = c.col_lo + l + col0;                 // column inside W
         static_for<0, C::E1>([&](auto K1) {
             constexpr int k1 = decltype(K1)::value;
-            const cf *wb = wr.p[k1 % C::CL];
-            x[k1] = wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gl];
+            if constexpr (CHUNK) {
+                x[k1] = c.S[(k1 * C::E2 + n2) * C::CP + lane];
+            } else {
+                const cf *wb = wr.p[k1 % C::CL];
+                x[k1] = wb[((k1 / C::CL) * C::E2 + n2) * C::WP + gl];
+            }
         });
         RegFFT<C::E1, true>::run(x);
         // sample n = E2*n1 + n2 is lag (n - shift) - yc -> surface row 2*(n-shift)+b
@@ -890,12 +925,27 @@ template <class C, bool IS_REF>
 SPX_HD void stage_in(const Ctx<C> &c, int tid, int chunk, int xoff) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
-    for (int k = warp; k < 32; k += C::NW) {
-        const int r = row_of<C, IS_REF>(c, chunk, k);
-        if (r < 0) continue;
-        const cf *src = c.W + r * C::WP;
-        cf *dst = c.S + k * C::SP + xoff;
-        for (int i = lane; i < nx; i += 32) dst[i] = src[i];
+    constexpr int NI = (C::NMAX + 31) / 32;      // elements of a row per lane
+    // two rows per iteration, every load of both issued before the first store (the slab
+    // is L2 / HBM resident: 2 * NI independent loads in flight per thread)
+    for (int k = warp; k < 32; k += 2 * C::NW) {
+        const int r0 = row_of<C, IS_REF>(c, chunk, k);
+        const int r1 = k + C::NW < 32 ? row_of<C, IS_REF>(c, chunk, k + C::NW) : -1;
+        const cf *s0 = c.W + (r0 >= 0 ? r0 : 0) * C::WP, *s1 = c.W + (r1 >= 0 ? r1 : 0) * C::WP;
+        cf v0[NI], v1[NI];
+        static_for<0, NI>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            const int i = lane + 32 * q;
+            v0[q] = (r0 >= 0 && i < nx) ? s0[i] : cmake(0.f, 0.f);
+            v1[q] = (r1 >= 0 && i < nx) ? s1[i] : cmake(0.f, 0.f);
+        });
+        cf *d0 = c.S + k * C::SP + xoff, *d1 = c.S + (k + C::NW) * C::SP + xoff;
+        static_for<0, NI>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            const int i = lane + 32 * q;
+            if (r0 >= 0 && i < nx) d0[i] = v0[q];
+            if (r1 >= 0 && i < nx) d1[i] = v1[q];
+        });
     }
 }
 template <class C>
@@ -909,6 +959,48 @@ SPX_HD void stage_out(const Ctx<C> &c, int tid, int chunk, int shift) {
         cf *dst = c.W + r * C::WP;
         for (int l = lane; l < nx; l += 32) dst[l] = src[l];
     }
+}
+
+// Fused column passes (C::FUSE): one 32-column chunk of W lives in S as [PL][CP]
+// (column = lane) between C1 and C2 resp. IC1 and IC2; these copies move it to / from the
+// slab - one warp per row, 256-byte row segments (chunk_in issues all loads of a thread
+// before its stores).  The reference only needs the rows with ky <= P/2 (its row stage skips the rest).
+template <class C, bool IS_REF>
+SPX_HD void chunk_out(const Ctx<C> &c, int tid, int chunk, int col0) {
+    const int warp = warp_of(tid), lane = tid & 31;
+    const int col = chunk * 32 + lane;
+    if (col >= c.ps->nx) return;
+    constexpr int RW = (C::PL + C::NW - 1) / C::NW;
+    cf *dst = c.W + col + col0;
+    static_for<0, RW>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        const int r = warp + C::NW * k;                       // warp-uniform
+        if (r < C::PL && (!IS_REF || ky_of_row<C>(r, 0) <= C::P / 2))
+            dst[r * C::WP] = c.S[r * C::CP + lane];
+    });
+}
+template <class C>
+SPX_HD void chunk_in(const Ctx<C> &c, int tid, int chunk, int col0) {
+    const int warp = warp_of(tid), lane = tid & 31;
+    const int col = chunk * 32 + lane;
+    const bool ok = col < c.ps->nx;
+    constexpr int RW = (C::PL + C::NW - 1) / C::NW;          // rows per warp
+    constexpr int G = RW < 16 ? RW : 16;                     // loads in flight per thread
+    const cf *src = c.W + (ok ? col + col0 : 0);
+    static_for<0, (RW + G - 1) / G>([&](auto GG) {
+        constexpr int g = decltype(GG)::value;
+        cf v[G];
+        static_for<0, G>([&](auto K) {
+            constexpr int k = g * G + decltype(K)::value;
+            const int r = warp + C::NW * k;
+            v[k - g * G] = (ok && k < RW && r < C::PL) ? src[r * C::WP] : cmake(0.f, 0.f);
+        });
+        static_for<0, G>([&](auto K) {
+            constexpr int k = g * G + decltype(K)::value;
+            const int r = warp + C::NW * k;
+            if (k < RW && r < C::PL) c.S[r * C::CP + lane] = v[k - g * G];
+        });
+    });
 }
 
 // X1: E1-point FFT along x of the nx input samples (padded position m = E2*n1+n2,
@@ -1247,10 +1339,25 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
     PairState *ps = c.ps;
     const int b = IT & 1;
     const int lz = (lazy && IT < 2) ? (b == 0 ? kLazyDetect : 1) : 0;
-    ex.par([&](int tid) {
-        const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin, lz);
-        if (fl) ex.or_status(&ps->status, fl);
-    });
+    [[maybe_unused]] const int nch = ((FAST ? C::NMAX : ps->nx) + 31) >> 5;    // 32-column chunks
+    if constexpr (C::FUSE) {
+        // C1 -> C2 -> slab, chunk by chunk through S (W is written once, finished)
+        SPX_NO_UNROLL
+        for (int j = 0; j < nch; ++j) {
+            ex.par([&](int tid) {
+                const int fl = c1_pass<C, FAST, false, CHECK, true>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff,
+                                                                    cin, lz, j);
+                if (fl) ex.or_status(&ps->status, fl);
+            });
+            ex.par([&](int tid) { c2_pass<C, FAST, true>(c, tid, cin, j); });
+            ex.par([&](int tid) { chunk_out<C, false>(c, tid, j, cin); });
+        }
+    } else {
+        ex.par([&](int tid) {
+            const int fl = c1_pass<C, FAST, false, CHECK>(c, tid, 1 + 2 * b, 2 + 2 * b, yoff, cin, lz);
+            if (fl) ex.or_status(&ps->status, fl);
+        });
+    }
     if (C::CL > 1) ex.cluster_sync();       // the peer's half of my rows has arrived
     // (the detector keys of both CTAs are complete after this barrier; every thread
     // evaluates the same few comparisons, so the branch is uniform)
@@ -1258,7 +1365,7 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
     // staged tiles: every thread is past its last tile read (the barrier that ended this C1
     // pass) and the pair will not be restarted any more: the next pair's copy may overwrite them
     if (C::STAGE && IT == 1) ex.tiles_release();
-    ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, cin); });
+    if (!C::FUSE) ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, cin); });
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
         ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
@@ -1272,19 +1379,36 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
             if (!C::DIRECT) ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
         }
     }
-    ex.par([&](int tid) { ic1_pass<C, FAST>(c, tid, cout); });
-    if (C::CL > 1) ex.cluster_sync();       // the peer's rows hold their lags: IC2 may read them
     // W now holds this pair's surface (keep).  After the first pair the warp that finishes
     // the argmax also saves the window around the best sample of that pair, before the
     // barrier that lets the next C1 pass overwrite W.
-    ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C, FAST>(c, tid, b, ysh, cout); },
-                        [&](int lane) {
+    auto after = [&](int lane) {
         if (!keep) return;
         if (lane == 0) { ps->in_w = b; ps->ysh = ysh; ps->cout = cout; }
         if (IT != 0) return;
         const int kc = (ps->best.idx / (2 * ps->nx)) >> 1, lc = (ps->best.idx % (2 * ps->nx)) >> 1;
         for (int t = lane; t < kWinN * kWinN; t += 32) save_window<C>(c, 0, kc, lc, t, ysh, cout);
-    });
+    };
+    if constexpr (C::FUSE) {
+        // slab -> IC1 -> IC2, chunk by chunk through S; every thread keeps its running best
+        // over the chunks (the merge is order independent: larger value, then smaller index)
+        Best acc = best_init();
+        SPX_NO_UNROLL
+        for (int j = 0; j < nch; ++j) {
+            ex.par([&](int tid) { chunk_in<C>(c, tid, j, cout); });
+            ex.par([&](int tid) { ic1_pass<C, FAST, true>(c, tid, cout, j); });
+            ex.par([&](int tid) {
+                const Best t = ic2_pass<C, FAST, true>(c, tid, b, ysh, cout, j);
+                if (best_better(t, acc)) acc = t;
+            });
+        }
+        ex.reduce_best_into(&ps->best, [&](int) { return acc; }, after);
+    } else {
+        ex.par([&](int tid) { ic1_pass<C, FAST>(c, tid, cout); });
+        if (C::CL > 1) ex.cluster_sync();   // the peer's rows hold their lags: IC2 may read them
+        ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C, FAST>(c, tid, b, ysh, cout); },
+                            after);
+    }
     // the peer must not start writing my rows (its next C1) while I still read
     // them; after the second pair the exchange barrier of the peak stage does that
     if (C::CL > 1 && b == 0) ex.cluster_sync();
@@ -1308,16 +1432,30 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
     const int cin = C::INPLACE ? xoff : 0, cout = C::INPLACE ? xsh : 0;
 
     // ---- reference image -> conj(R) * scale, half spectrum ---------------
-    ex.par([&](int tid) {
-#ifdef SPX_LAZY_NOREF                    // developer knob: cost of the reference-side detector
-        const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0, lazy ? 1 : 0);
+#ifdef SPX_LAZY_NOREF                        // developer knob: cost of the reference-side detector
+    const int lzr = lazy ? 1 : 0;
 #else
-        const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0, lazy ? kLazyDetect : 0);
+    const int lzr = lazy ? kLazyDetect : 0;
 #endif
-        if (fl) ex.or_status(&ps->status, fl);
-    });
-    if (C::CL > 1) ex.cluster_sync();           // the peer's half of my rows has arrived
-    ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, 0); });
+    if constexpr (C::FUSE) {
+        const int nch = ((FAST ? C::NMAX : ps->nx) + 31) >> 5;
+        SPX_NO_UNROLL
+        for (int j = 0; j < nch; ++j) {
+            ex.par([&](int tid) {
+                const int fl = c1_pass<C, FAST, true, CHECK, true>(c, tid, 0, -1, 0, 0, lzr, j);
+                if (fl) ex.or_status(&ps->status, fl);
+            });
+            ex.par([&](int tid) { c2_pass<C, FAST, true>(c, tid, 0, j); });
+            ex.par([&](int tid) { chunk_out<C, true>(c, tid, j, 0); });
+        }
+    } else {
+        ex.par([&](int tid) {
+            const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0, lzr);
+            if (fl) ex.or_status(&ps->status, fl);
+        });
+        if (C::CL > 1) ex.cluster_sync();       // the peer's half of my rows has arrived
+        ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, 0); });
+    }
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, 0, C::RCHUNK, 0); });
         ex.par([&](int tid) { x2_ref_pass<C>(c, tid, 0, C::RCHUNK); });

@@ -93,13 +93,21 @@ def test_results_do_not_depend_on_the_thread_order(emu, case):
 
 
 def test_cluster_and_slab_forms_of_the_large_classes_agree(emu):
-    """170 / 256 px: the cluster forms (shared memory, DSMEM) and the global-slab forms run
-    the same arithmetic in the same order - bit-identical results."""
-    for ny, nx in ((170, 170), (256, 256)):
-        stacks, _ = orc.random_pairs(1, ny, nx, seed=ny)
-        a = emu(stacks, 1)
-        b = emu(stacks, 1, env={"SPX_EMU_SLAB": "1"})
-        assert all(np.array_equal(x, y) for x, y in zip(a, b)), (ny, nx)
+    """170 / 256 px: the cluster forms (shared memory, DSMEM) and the global-slab forms (the
+    device default: column passes fused chunk by chunk through the scratch S, two CTAs of 8
+    warps per SM) run the same arithmetic in the same order - bit-identical results, for
+    full and ragged shapes, with and without a requested surface, in any thread order."""
+    for ny, nx, masked in ((170, 170, False), (256, 256, False), (150, 129, True), (200, 256, True),
+                           (131, 33, False)):
+        stacks, _ = orc.random_pairs(1, ny, nx, seed=ny, masked=masked)
+        for t, no_icc in ((1, 0), (1, 1), (2, 0)):
+            a = emu(stacks, t, no_icc=no_icc)
+            b = emu(stacks, t, no_icc=no_icc, env={"SPX_EMU_SLAB": "1"})
+            assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])), (ny, nx, t, no_icc)
+            if not no_icc:
+                assert np.array_equal(a[3], b[3])
+        c = emu(stacks, 2, env={"SPX_EMU_SLAB": "1", "SPX_EMU_ORDER": "2"})
+        assert all(np.array_equal(x, y) for x, y in zip(b, c)), (ny, nx)
 
 
 def test_statistics_free_ncc_path(emu):

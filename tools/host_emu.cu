@@ -143,14 +143,14 @@ int main(int argc, char **argv) {
     if (m <= 20) run<CcCfg<32, 4, 8, 20, 64, 12, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 32 && m <= 42) run<CcCfg<64, 8, 8, 42, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 64 && m <= 84) run<CcCfg<128, 8, 16, 84, 512, 1, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
-    else if (m > 128 && m <= 170 && slab) run<CcCfg<256, 16, 16, 170, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (m > 128 && m <= 170 && slab) run<CcCfg<256, 16, 16, 170, 256, 2, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m > 128 && m <= 170) run<CcCfg<256, 16, 16, 170, 512, 1, true, true, true, 4>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 32 && stage && ny == 32 && nx == 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true, 1, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 64 && m > 42 && stage && ny == 64 && nx == 64) run<CcCfg<96, 12, 8, 64, 512, 1, true, true, true, 1, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 32) run<CcCfg<48, 6, 8, 32, 128, 4, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 64) run<CcCfg<96, 12, 8, 64, 256, 2, true, true, true>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else if (m <= 128) run<CcCfg<192, 12, 16, 128, 512, 1, true, true, EMU128_INPLACE, 2>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
-    else if (slab) run<CcCfg<384, 24, 16, 256, 512, 1, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
+    else if (slab) run<CcCfg<384, 24, 16, 256, 256, 2, false, false>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     else run<CcCfg<384, 24, 16, 256, 384, 1, true, true, true, 8>>(n, ny, nx, cc_type, stack.data(), shifts.data(), peak.data(), status.data(), icc.data());
     f = fopen(argv[2], "wb");
     fwrite(shifts.data(), 8, shifts.size(), f);

@@ -1003,6 +1003,52 @@ SPX_HD void chunk_in(const Ctx<C> &c, int tid, int chunk, int col0) {
     });
 }
 
+// L2 prefetches for the slab classes: the next row batch / column chunk of W (and the R rows
+// its X2 pass will read) is pulled from HBM into L2 while the current one is transformed, so
+// the copy passes pay the L2 latency instead of the DRAM latency.  -DSPX_NO_SLAB_PREFETCH=1
+// switches them off (A/B knob).
+SPX_HD void l2_prefetch(const void *p) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU) && !defined(SPX_NO_SLAB_PREFETCH)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+// the 128-byte lines of [p, p + bytes), dealt to the lanes of a warp
+SPX_HD void l2_prefetch_span(const void *p, int bytes, int lane) {
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU)
+    const unsigned long long lo = reinterpret_cast<unsigned long long>(p), hi = lo + bytes;
+    for (unsigned long long q = (lo & ~127ull) + 128ull * lane; q < hi; q += 128ull * 32)
+        l2_prefetch(reinterpret_cast<const void *>(q));
+#else
+    (void)p; (void)bytes; (void)lane;
+#endif
+}
+template <class C, bool IS_REF>
+SPX_HD void prefetch_row_batch(const Ctx<C> &c, int tid, int chunk) {
+    if (chunk >= (IS_REF ? C::RCHUNK : C::NCHUNK)) return;
+    const int warp = warp_of(tid), lane = tid & 31;
+    const int nx = c.ps->nx;
+    for (int k = warp; k < 32; k += C::NW) {
+        const int r = row_of<C, IS_REF>(c, chunk, k);
+        if (r < 0) continue;
+        l2_prefetch_span(c.W + r * C::WP, nx * 8, lane);
+        if (!IS_REF) {                                       // the R row of x2_pass
+            const int ky = ky_of_row<C>(r, c.rank);
+            const int q = ky > C::P / 2 ? C::P - ky : ky;
+            l2_prefetch_span(c.R + rmap<C>(q) * C::RP, C::P * 8, lane);
+        }
+    }
+}
+template <class C>
+SPX_HD void prefetch_col_chunk(const Ctx<C> &c, int tid, int chunk, int col0) {
+    if (chunk * 32 >= c.ps->nx) return;
+    for (int r = tid; r < C::PL; r += C::T) {
+        const cf *p = c.W + r * C::WP + chunk * 32 + col0;   // 256 bytes: up to three lines
+        l2_prefetch(p); l2_prefetch(p + 16); l2_prefetch(p + 31);
+    }
+}
+
 // X1: E1-point FFT along x of the nx input samples (padded position m = E2*n1+n2,
 // input column m - xoff)
 template <class C, bool FAST, bool IS_REF>
@@ -1373,7 +1419,10 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
     } else {
         for (int k = 0; k < C::NCHUNK; ++k) {
             if (!C::DIRECT) ex.par([&](int tid) { stage_in<C, false>(c, tid, k, xoff); });
-            ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff); });
+            ex.par([&](int tid) {
+                if (C::FUSE) prefetch_row_batch<C, false>(c, tid, k + 1);
+                x1_pass<C, FAST, false>(c, tid, k, k + 1, xoff);
+            });
             ex.par([&](int tid) { x2_pass<C>(c, tid, k, k + 1); });
             ex.par([&](int tid) { x3_pass<C, FAST>(c, tid, k, k + 1, xsh); });
             if (!C::DIRECT) ex.par([&](int tid) { stage_out<C>(c, tid, k, xsh); });
@@ -1396,7 +1445,10 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
         SPX_NO_UNROLL
         for (int j = 0; j < nch; ++j) {
             ex.par([&](int tid) { chunk_in<C>(c, tid, j, cout); });
-            ex.par([&](int tid) { ic1_pass<C, FAST, true>(c, tid, cout, j); });
+            ex.par([&](int tid) {
+                prefetch_col_chunk<C>(c, tid, j + 1, cout);
+                ic1_pass<C, FAST, true>(c, tid, cout, j);
+            });
             ex.par([&](int tid) {
                 const Best t = ic2_pass<C, FAST, true>(c, tid, b, ysh, cout, j);
                 if (best_better(t, acc)) acc = t;
@@ -1462,7 +1514,10 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
     } else {
         for (int b = 0; b < C::RCHUNK; ++b) {
             if (!C::DIRECT) ex.par([&](int tid) { stage_in<C, true>(c, tid, b, 0); });
-            ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, b, b + 1, 0); });
+            ex.par([&](int tid) {
+                if (C::FUSE) prefetch_row_batch<C, true>(c, tid, b + 1);
+                x1_pass<C, FAST, true>(c, tid, b, b + 1, 0);
+            });
             ex.par([&](int tid) { x2_ref_pass<C>(c, tid, b, b + 1); });
         }
     }

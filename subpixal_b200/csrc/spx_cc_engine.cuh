@@ -120,7 +120,13 @@ struct CcCfg {
     static constexpr int NXL = (NMAX + CL - 1) / CL;   // tile columns loaded / finished by one CTA
     static constexpr int E1L = E1 / CL;      // k1 groups (of E2 rows each) held by one CTA
     static constexpr int PL = P / CL;        // rows of W held by one CTA
-    static constexpr int WP = INPLACE ? P + 1 : NMAX + 1;   // pitch of W (complex), odd
+    // pitch of W (complex): odd in shared memory (bank conflicts); in a global slab a
+    // multiple of 16 elements, so that rows and 32-column chunks start on 128-byte lines
+#ifndef SPX_SLAB_ODD_PITCH
+    static constexpr int WP = INPLACE ? P + 1 : (WSM_ ? NMAX + 1 : (NMAX + 15) / 16 * 16);
+#else
+    static constexpr int WP = INPLACE ? P + 1 : NMAX + 1;
+#endif
     // how the row stage reaches its rows: in place in W / directly in W (shared
     // memory, lanes along rows) / staged through S by coalesced copies (W global)
     static constexpr bool DIRECT = !INPLACE && WSM_;
@@ -135,7 +141,11 @@ struct CcCfg {
 #endif
     static constexpr int CP = 32;            // pitch of a column chunk held in S: [PL][32]
     static constexpr int SP = P + 1;         // pitch of the row scratch, odd
-    static constexpr int RP = P + 1;         // pitch of R, odd
+#ifndef SPX_SLAB_ODD_PITCH
+    static constexpr int RP = RSM_ ? P + 1 : P;   // pitch of R: odd in shared memory, whole lines in a slab
+#else
+    static constexpr int RP = P + 1;
+#endif
     static constexpr int RH = P / 2 + 1;     // rows of R (half spectrum)
     static constexpr int RHL = (RH + CL - 1) / CL;   // ... held by one CTA
     static constexpr int BATCH = 32;         // rows per row-op batch (= lanes)

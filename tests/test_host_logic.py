@@ -227,3 +227,29 @@ def test_scratch_cache_release():
         assert not batch._scratch_bufs and not batch._workspaces
     finally:
         torch.cuda.current_stream = orig
+
+
+def test_public_surface_matches_the_reference():
+    """Drop-in guard: every public attribute of the reference's Cutout, the builders'
+    signatures and the signatures of find_displacement / find_peak / parse_file_name are
+    the reference's own (checked live when the reference sources are present)."""
+    import inspect
+    from oracle import refload
+    if not refload.available():
+        pytest.skip("reference tree not present")
+    import subpixal_b200.cutout as mc
+    import subpixal_b200.cc as mcc
+    import subpixal_b200.centroid as mce
+    import subpixal_b200.ingest as mi
+    rc, rcc, rce, ru = (refload.load(n) for n in ("cutout", "cc", "centroid", "utils"))
+    public = lambda o: {n for n in dir(o) if not n.startswith("_")}      # noqa: E731
+    assert public(rc.Cutout) == public(mc.Cutout)
+    assert all(hasattr(mc, n) for n in rc.__all__)
+    for name in ("create_primary_cutouts", "create_cutouts", "create_input_image_cutouts",
+                 "drz_from_input_cutouts"):
+        assert str(inspect.signature(getattr(rc, name))) == str(inspect.signature(getattr(mc, name)))
+    assert str(inspect.signature(rc.Cutout.__init__)) == str(inspect.signature(mc.Cutout.__init__))
+    assert str(inspect.signature(rcc.find_displacement)) == str(inspect.signature(mcc.find_displacement))
+    assert str(inspect.signature(rce.find_peak)) == str(inspect.signature(mce.find_peak))
+    assert str(inspect.signature(ru.parse_file_name)) == str(inspect.signature(mi.parse_file_name))
+    assert issubclass(mc.NoOverlapError, ValueError) and issubclass(mc.PartialOverlapError, ValueError)

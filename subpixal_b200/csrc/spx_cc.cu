@@ -319,6 +319,8 @@ struct DevExec {
         if (threadIdx.x == 0 && next_pair >= 0) tiles_issue(next_pair);
     }
     __device__ __forceinline__ void cluster_sync() { cg::this_cluster().sync(); }
+    __device__ __forceinline__ void cluster_arrive() { cg::this_cluster().barrier_arrive(); }
+    __device__ __forceinline__ void cluster_wait() { cg::this_cluster().barrier_wait(); }
     __device__ __forceinline__ void global_fence() { __threadfence(); }
     __device__ __forceinline__ void or_status(int *p, int v) { atomicOr(p, v); }
     __device__ __forceinline__ float load_icc(const float *p) { return __ldcg(p); }

@@ -140,6 +140,16 @@ struct CcCfg {
     static constexpr bool FUSE = false;
 #endif
     static constexpr int CP = 32;            // pitch of a column chunk held in S: [PL][32]
+    // cluster classes whose column split falls on 32-column chunks: SPLIT-PHASE cluster
+    // barriers around the two column passes that need the peers' rows.  After C1 a CTA
+    // arrives, runs C2 on the columns it loaded itself (written by nobody else) and only then
+    // waits for the peers' stores; before IC2 it runs IC1 on the PEERS' columns first,
+    // arrives, finishes its own columns and waits - half a pass of slack per barrier.
+#ifndef SPX_NO_SPLIT_SYNC
+    static constexpr bool SPLIT = CL_ > 1 && ((NMAX_ + CL_ - 1) / CL_) % 32 == 0;
+#else
+    static constexpr bool SPLIT = false;
+#endif
     static constexpr int SP = P + 1;         // pitch of the row scratch, odd
 #ifndef SPX_SLAB_ODD_PITCH
     static constexpr int RP = RSM_ ? P + 1 : P;   // pitch of R: odd in shared memory, whole lines in a slab
@@ -772,14 +782,17 @@ SPX_HD bool lazy_decide(const unsigned (&det)[2], bool need_evidence) {
 
 // C2: E2-point FFT over n2 for every (column, k1 group of mine), in place.
 // (FAST: full-size tile - nx, ny and the surface width are compile-time constants)
+// (ch_lo, ch_hi: only the 32-column chunks [ch_lo, ch_hi) - split-phase cluster barriers)
 template <class C, bool FAST = false, bool CHUNK = false>
-SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0) {
+SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0, int ch_lo = 0, int ch_hi = 1 << 20) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
     constexpr int WPc = CHUNK ? C::CP : C::WP;
     cf *wbase = CHUNK ? c.S : c.W;
-    const int item0 = CHUNK ? chunk * C::E1L : 0, item1 = CHUNK ? (chunk + 1) * C::E1L : nchunk * C::E1L;
+    if (ch_hi > nchunk) ch_hi = nchunk;
+    const int item0 = CHUNK ? chunk * C::E1L : ch_lo * C::E1L;
+    const int item1 = CHUNK ? (chunk + 1) * C::E1L : ch_hi * C::E1L;
     SPX_UNROLL_SMALL
     for (int wi = item0 + warp; wi < item1; wi += C::NW) {
         const int j = wi % C::E1L, i = (wi / C::E1L) * 32 + lane;
@@ -800,13 +813,15 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0) {
 
 // IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
 template <class C, bool FAST = false, bool CHUNK = false>
-SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0) {
+SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0, int ch_lo = 0, int ch_hi = 1 << 20) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : c.ps->nx;
     const int nchunk = (nx + 31) >> 5;
     constexpr int WPc = CHUNK ? C::CP : C::WP;
     cf *wbase = CHUNK ? c.S : c.W;
-    const int item0 = CHUNK ? chunk * C::E1L : 0, item1 = CHUNK ? (chunk + 1) * C::E1L : nchunk * C::E1L;
+    if (ch_hi > nchunk) ch_hi = nchunk;
+    const int item0 = CHUNK ? chunk * C::E1L : ch_lo * C::E1L;
+    const int item1 = CHUNK ? (chunk + 1) * C::E1L : ch_hi * C::E1L;
     SPX_UNROLL_SMALL
     for (int wi = item0 + warp; wi < item1; wi += C::NW) {
         const int j = wi % C::E1L, l = (wi / C::E1L) * 32 + lane;
@@ -1414,14 +1429,24 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
             if (fl) ex.or_status(&ps->status, fl);
         });
     }
-    if (C::CL > 1) ex.cluster_sync();       // the peer's half of my rows has arrived
+    // my 32-column chunks (the tile columns this CTA loaded): [m0, m1)
+    [[maybe_unused]] const int m0 = c.rank * (C::NXL / 32), m1 = m0 + C::NXL / 32;
+    if (C::SPLIT) {
+        ex.cluster_arrive();                // my stores into the peers' rows are on their way
+        ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, cin, 0, m0, m1); });
+        ex.cluster_wait();                  // the peers' part of my rows has arrived
+    } else if (C::CL > 1) ex.cluster_sync();
     // (the detector keys of both CTAs are complete after this barrier; every thread
     // evaluates the same few comparisons, so the branch is uniform)
     if (lazy && IT < 2 && !lazy_decide(c.xl->det[c.dslot], b == 0)) return false;
     // staged tiles: every thread is past its last tile read (the barrier that ended this C1
     // pass) and the pair will not be restarted any more: the next pair's copy may overwrite them
     if (C::STAGE && IT == 1) ex.tiles_release();
-    if (!C::FUSE) ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, cin); });
+    if (C::SPLIT) ex.par([&](int tid) {
+        c2_pass<C, FAST>(c, tid, cin, 0, 0, m0);
+        c2_pass<C, FAST>(c, tid, cin, 0, m1);
+    });
+    else if (!C::FUSE) ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, cin); });
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, false>(c, tid, 0, C::NCHUNK, xoff); });
         ex.par([&](int tid) { x2_pass<C>(c, tid, 0, C::NCHUNK); });
@@ -1466,8 +1491,18 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
         }
         ex.reduce_best_into(&ps->best, [&](int) { return acc; }, after);
     } else {
-        ex.par([&](int tid) { ic1_pass<C, FAST>(c, tid, cout); });
-        if (C::CL > 1) ex.cluster_sync();   // the peer's rows hold their lags: IC2 may read them
+        if (C::SPLIT) {
+            ex.par([&](int tid) {           // the columns the peers' IC2 will read from my rows
+                ic1_pass<C, FAST>(c, tid, cout, 0, 0, m0);
+                ic1_pass<C, FAST>(c, tid, cout, 0, m1);
+            });
+            ex.cluster_arrive();
+            ex.par([&](int tid) { ic1_pass<C, FAST>(c, tid, cout, 0, m0, m1); });
+            ex.cluster_wait();              // the peers' rows hold the lags of my columns
+        } else {
+            ex.par([&](int tid) { ic1_pass<C, FAST>(c, tid, cout); });
+            if (C::CL > 1) ex.cluster_sync();   // the peer's rows hold their lags: IC2 may read them
+        }
         ex.reduce_best_into(&ps->best, [&](int tid) { return ic2_pass<C, FAST>(c, tid, b, ysh, cout); },
                             after);
     }
@@ -1515,8 +1550,19 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
             const int fl = c1_pass<C, FAST, true, CHECK>(c, tid, 0, -1, 0, 0, lzr);
             if (fl) ex.or_status(&ps->status, fl);
         });
-        if (C::CL > 1) ex.cluster_sync();       // the peer's half of my rows has arrived
-        ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, 0); });
+        if (C::SPLIT) {
+            const int m0 = c.rank * (C::NXL / 32), m1 = m0 + C::NXL / 32;
+            ex.cluster_arrive();
+            ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, 0, 0, m0, m1); });
+            ex.cluster_wait();
+            ex.par([&](int tid) {
+                c2_pass<C, FAST>(c, tid, 0, 0, 0, m0);
+                c2_pass<C, FAST>(c, tid, 0, 0, m1);
+            });
+        } else {
+            if (C::CL > 1) ex.cluster_sync();   // the peer's half of my rows has arrived
+            ex.par([&](int tid) { c2_pass<C, FAST>(c, tid, 0); });
+        }
     }
     if (C::INPLACE) {
         ex.par([&](int tid) { x1_pass<C, FAST, true>(c, tid, 0, C::RCHUNK, 0); });
@@ -1573,6 +1619,7 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
 //   warp_fit(lane_f, final_f) one warp: sum lane_f(lane) over 32 lanes, then
 //                   final_f(sum) on one lane, then barrier
 //   cluster_sync()  barrier over all CTAs of a cluster (CL > 1 only)
+//   cluster_arrive() / cluster_wait()  the two halves of such a barrier (split phase)
 //   tiles_wait()    (STAGE) block until the staged tiles of the current pair have landed
 //   tiles_release() (STAGE) the tiles were read for the last time: start staging the next pair
 //   global_fence()  make this thread block's global writes visible to the peer

@@ -54,6 +54,8 @@ struct HostExec {
     void tiles_release() { if (next_src) for (size_t i = 0; i < tile_floats; ++i) tiles[i] = next_src[i]; }
     pthread_barrier_t *bar = nullptr;          // cluster barrier (two host threads = two CTAs)
     void cluster_sync() { pthread_barrier_wait(bar); }
+    void cluster_arrive() {}                             // split phase: the wait is the barrier
+    void cluster_wait() { pthread_barrier_wait(bar); }
     void global_fence() {}
     void or_status(int *p, int v) { *p |= v; }
     float load_icc(const float *p) { return *p; }

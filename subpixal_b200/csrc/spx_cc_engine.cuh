@@ -593,6 +593,12 @@ SPX_HD int c1_pass(const Ctx<C> &c, int tid, int sa, int sb, int yoff, int col0,
         const int rs = C::E2 * ta.pitch;                     // elements between loads
         const float *pa0 = ta.p + ybase * ta.pitch;
         const float *pb0 = tb.p + ybase * tb.pitch;
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU) && !defined(SPX_NO_OPAQUE_PTR)
+        // keep the two column pointers as materialised 64-bit byte addresses: each load is then
+        // pointer + warp-uniform offset (two integer instructions) instead of the
+        // (index + offset) * 4 + base the compiler re-associates to (four per load)
+        asm volatile("" : "+l"(pa0), "+l"(pb0));
+#endif
         static_for<0, C::E1>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
             // generic path: the rows that exist depend on the item, so every row is a candidate

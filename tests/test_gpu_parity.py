@@ -452,3 +452,31 @@ def test_surface_kept_on_chip_matches_requested_surface():
             else:
                 assert torch.equal(kept[0], full[0]), (n, t)
         assert n < 32 or int(kept[1][0]) // (2 * n) % 2 == 1     # the decoy case peaks on an odd row
+
+
+@pytest.mark.gpu
+def test_slab_classes_ragged_shapes_vs_oracle():
+    """170 / 256 px classes (global-slab form with the column passes fused per 32-column
+    chunk): shapes whose width is not a multiple of the chunk, very narrow / very flat
+    cutouts, masked pixels - shift, peak index and surface against the oracle."""
+    import torch
+    from subpixal_b200 import batch
+    shapes = [(256, 256), (129, 129), (171, 171), (256, 3), (3, 256), (200, 31), (33, 250),
+              (170, 129), (255, 255), (131, 33), (160, 97), (256, 65), (65, 256), (224, 160)]
+    stacks = [orc.random_pairs(1, ny, nx, seed=900 + k, masked=(k % 3 == 0))[0][0]
+              for k, (ny, nx) in enumerate(shapes)]
+    flat = np.concatenate([s.ravel() for s in stacks]).astype(np.float32)
+    off = np.concatenate([[0], np.cumsum([s.size for s in stacks])])[:-1]
+    for cc_type, want in (("NCC", False), ("NCC", True), ("ZNCC", True)):
+        res = batch.cc_fit_ragged(torch.from_numpy(flat).cuda(), off, np.array(shapes), cc_type,
+                                  want_icc=want)
+        sh, pk, st = (r.cpu().numpy() for r in res[:3])
+        for k, (ny, nx) in enumerate(shapes):
+            with warnings.catch_warnings(), np.errstate(all="ignore"):
+                warnings.simplefilter("ignore")
+                dx, dy, icc, _ = orc.find_displacement(*stacks[k], cc_type=cc_type, full_output=True)
+            assert int(np.argmax(icc)) == pk[k] and st[k] == 0, (cc_type, ny, nx)
+            assert abs(sh[k, 0] - dx) < 5e-5 and abs(sh[k, 1] - dy) < 5e-5, (cc_type, ny, nx)
+            if want:
+                got = res[3][int(res[4][k]):int(res[4][k + 1])].cpu().numpy().reshape(2 * ny, 2 * nx)
+                assert np.linalg.norm(got - icc) <= 1e-5 * np.linalg.norm(icc), (cc_type, ny, nx)

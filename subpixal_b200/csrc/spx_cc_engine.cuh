@@ -940,6 +940,16 @@ template <class C, bool IS_REF>
 SPX_HD int row_of(const Ctx<C> &c, int chunk, int lane) {
     const int k = chunk * 32 + lane;
     if (IS_REF) return k < c.n_rrow ? int(c.rrow[k]) : -1;
+#ifndef SPX_NO_ROW_PAIRING
+    if constexpr (C::FUSE && C::E2 == 16 && C::E1 % 2 == 0) {
+        // slab classes: a batch is the k1 group g together with group E1 - g (0 with E1/2):
+        // row (k1, k2) holds ky = k1 + E1*k2 and row (E1 - k1, E2 - 1 - k2) holds P - ky, so
+        // the two rows that read the same R row (direct and mirrored) sit in the SAME batch
+        // and R comes from HBM once per phase pair instead of twice
+        const int g = lane < 16 ? (chunk == 0 ? 0 : chunk) : (chunk == 0 ? C::E1 / 2 : C::E1 - chunk);
+        return g * 16 + (lane & 15);
+    }
+#endif
     return k < C::PL ? k : -1;
 }
 // row of the (local part of the) stored half spectrum that holds frequency row q
@@ -1174,6 +1184,24 @@ SPX_HD void x2_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         const int col_d = k1 * C::E2;
         const int col_f = k1 ? (C::E1 - k1) * C::E2 + C::E2 - 1 : C::E2;
         const cf *Rd = Rrow + (flip ? col_f : col_d);
+#if defined(__CUDA_ARCH__) && !defined(SPX_HOST_EMU) && !defined(SPX_NO_R128)
+        // R in a global slab (line pitch, so every k1 block of a row is 16-byte aligned): two
+        // values per 128-bit load.  A mirrored row reads the block (E1-k1)*E2 .. +E2-1 backwards:
+        // the pair at 14-2j holds the values for k2 = 2j+1 and 2j (k1 = 0 mixes element 0 in and
+        // keeps the scalar loads).
+        if (!C::R_SMEM && C::RP % 2 == 0 && C::E2 % 2 == 0 && k1 != 0) {
+            const float4 *Rq = reinterpret_cast<const float4 *>(
+                Rrow + (flip ? (C::E1 - k1) * C::E2 : col_d));
+            static_for<0, C::E2 / 2>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                const float4 q = Rq[flip ? C::E2 / 2 - 1 - j : j];      // (R is written by this kernel: no ld.nc)
+                cf v0 = flip ? cmake(q.z, -q.w) : cmake(q.x, q.y);     // k2 = 2j
+                cf v1 = flip ? cmake(q.x, -q.y) : cmake(q.z, q.w);     // k2 = 2j + 1
+                x[2 * j] = cmul(x[2 * j], v0);
+                x[2 * j + 1] = cmul(x[2 * j + 1], v1);
+            });
+        } else
+#endif
         static_for<0, C::E2>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
             cf v = flip ? ((k1 == 0 && k2 == 0) ? Rrow[0] : Rd[-k2]) : Rd[k2];

@@ -475,7 +475,8 @@ def test_slab_classes_ragged_shapes_vs_oracle():
             with warnings.catch_warnings(), np.errstate(all="ignore"):
                 warnings.simplefilter("ignore")
                 dx, dy, icc, _ = orc.find_displacement(*stacks[k], cc_type=cc_type, full_output=True)
-            assert int(np.argmax(icc)) == pk[k] and st[k] == 0, (cc_type, ny, nx)
+            # (fall-back bits such as NO_MAXIMUM are legitimate: a 3 px wide surface)
+            assert int(np.argmax(icc)) == pk[k] and (st[k] & 0x3f) == 0, (cc_type, ny, nx)
             assert abs(sh[k, 0] - dx) < 5e-5 and abs(sh[k, 1] - dy) < 5e-5, (cc_type, ny, nx)
             if want:
                 got = res[3][int(res[4][k]):int(res[4][k + 1])].cpu().numpy().reshape(2 * ny, 2 * nx)

@@ -962,10 +962,43 @@ SPX_HD cf *srow_of(const Ctx<C> &c, int r, int lane) {
 // Staged mode (W in global memory): coalesced copy of one batch of rows between
 // W (columns = input / lag index) and the scratch S (columns = padded position);
 // one warp per row, lanes along the row.
+// slab classes with a line pitch: the global side of the copies moves two values per access
+template <class C> struct Wide128 {
+#ifndef SPX_NO_WIDE_COPIES
+    static constexpr bool value = !C::W_SMEM && !C::INPLACE && C::WP % 2 == 0 && C::CL == 1;
+#else
+    static constexpr bool value = false;
+#endif
+};
 template <class C, bool IS_REF>
 SPX_HD void stage_in(const Ctx<C> &c, int tid, int chunk, int xoff) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = c.ps->nx;
+    if constexpr (Wide128<C>::value) {
+        constexpr int NP = ((C::NMAX + 1) / 2 + 31) / 32;    // value PAIRS of a row per lane
+        for (int k = warp; k < 32; k += 2 * C::NW) {
+            const int r0 = row_of<C, IS_REF>(c, chunk, k);
+            const int r1 = k + C::NW < 32 ? row_of<C, IS_REF>(c, chunk, k + C::NW) : -1;
+            const cf2 *s0 = reinterpret_cast<const cf2 *>(c.W + (r0 >= 0 ? r0 : 0) * C::WP);
+            const cf2 *s1 = reinterpret_cast<const cf2 *>(c.W + (r1 >= 0 ? r1 : 0) * C::WP);
+            cf2 v0[NP], v1[NP];
+            static_for<0, NP>([&](auto Q) {
+                constexpr int q = decltype(Q)::value;
+                const int i = lane + 32 * q;
+                cf2 z; z.a = z.b = cmake(0.f, 0.f);
+                v0[q] = (r0 >= 0 && 2 * i < nx) ? s0[i] : z;
+                v1[q] = (r1 >= 0 && 2 * i < nx) ? s1[i] : z;
+            });
+            cf *d0 = c.S + k * C::SP + xoff, *d1 = c.S + (k + C::NW) * C::SP + xoff;
+            static_for<0, NP>([&](auto Q) {
+                constexpr int q = decltype(Q)::value;
+                const int i = 2 * (lane + 32 * q);
+                if (r0 >= 0 && i < nx) { d0[i] = v0[q].a; if (i + 1 < nx) d0[i + 1] = v0[q].b; }
+                if (r1 >= 0 && i < nx) { d1[i] = v1[q].a; if (i + 1 < nx) d1[i + 1] = v1[q].b; }
+            });
+        }
+        return;
+    }
     constexpr int NI = (C::NMAX + 31) / 32;      // elements of a row per lane
     // two rows per iteration, every load of both issued before the first store (the slab
     // is L2 / HBM resident: 2 * NI independent loads in flight per thread)
@@ -998,7 +1031,15 @@ SPX_HD void stage_out(const Ctx<C> &c, int tid, int chunk, int shift) {
         if (r < 0) continue;
         const cf *src = c.S + k * C::SP + shift;
         cf *dst = c.W + r * C::WP;
-        for (int l = lane; l < nx; l += 32) dst[l] = src[l];
+        if constexpr (Wide128<C>::value) {
+            // (an odd nx writes one value past the row's last lag: inside the pitch, never read)
+            for (int l = 2 * lane; l < nx; l += 64) {
+                cf2 v; v.a = src[l]; v.b = src[l + 1];
+                *reinterpret_cast<cf2 *>(dst + l) = v;
+            }
+        } else {
+            for (int l = lane; l < nx; l += 32) dst[l] = src[l];
+        }
     }
 }
 
@@ -1009,6 +1050,20 @@ SPX_HD void stage_out(const Ctx<C> &c, int tid, int chunk, int shift) {
 template <class C, bool IS_REF>
 SPX_HD void chunk_out(const Ctx<C> &c, int tid, int chunk, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
+    if constexpr (Wide128<C>::value && C::PL % (2 * C::NW) == 0) {
+        // half a warp per row, two values per lane: 512 contiguous bytes of S, 2 x 256 of W
+        const int half = lane >> 4, col = chunk * 32 + 2 * (lane & 15);
+        if (col >= c.ps->nx) return;
+        constexpr int RW = C::PL / (2 * C::NW);
+        static_for<0, RW>([&](auto K) {
+            constexpr int k = decltype(K)::value;
+            const int r = 2 * (warp + C::NW * k) + half;
+            if (!IS_REF || ky_of_row<C>(r, 0) <= C::P / 2)
+                *reinterpret_cast<cf2 *>(c.W + r * C::WP + col + col0) =
+                    *reinterpret_cast<const cf2 *>(c.S + r * C::CP + 2 * (lane & 15));
+        });
+        return;
+    }
     const int col = chunk * 32 + lane;
     if (col >= c.ps->nx) return;
     constexpr int RW = (C::PL + C::NW - 1) / C::NW;
@@ -1023,6 +1078,30 @@ SPX_HD void chunk_out(const Ctx<C> &c, int tid, int chunk, int col0) {
 template <class C>
 SPX_HD void chunk_in(const Ctx<C> &c, int tid, int chunk, int col0) {
     const int warp = warp_of(tid), lane = tid & 31;
+    if constexpr (Wide128<C>::value && C::PL % (2 * C::NW) == 0) {
+        const int half = lane >> 4, col = chunk * 32 + 2 * (lane & 15);
+        const bool ok = col < c.ps->nx;
+        constexpr int RW = C::PL / (2 * C::NW);               // row pairs per warp
+        constexpr int G = RW < 12 ? RW : 12;                  // 128-bit loads in flight per thread
+        const cf *src = c.W + (ok ? col + col0 : 0);
+        static_for<0, (RW + G - 1) / G>([&](auto GG) {
+            constexpr int g = decltype(GG)::value;
+            cf2 v[G];
+            static_for<0, G>([&](auto K) {
+                constexpr int k = g * G + decltype(K)::value;
+                const int r = 2 * (warp + C::NW * k) + half;
+                cf2 z; z.a = z.b = cmake(0.f, 0.f);
+                v[k - g * G] = (ok && k < RW) ? *reinterpret_cast<const cf2 *>(src + r * C::WP) : z;
+            });
+            static_for<0, G>([&](auto K) {
+                constexpr int k = g * G + decltype(K)::value;
+                const int r = 2 * (warp + C::NW * k) + half;
+                if (ok && k < RW)
+                    *reinterpret_cast<cf2 *>(c.S + r * C::CP + 2 * (lane & 15)) = v[k - g * G];
+            });
+        });
+        return;
+    }
     const int col = chunk * 32 + lane;
     const bool ok = col < c.ps->nx;
     constexpr int RW = (C::PL + C::NW - 1) / C::NW;          // rows per warp
@@ -1149,6 +1228,15 @@ SPX_HD void x2_ref_pass(const Ctx<C> &c, int tid, int cb, int ce) {
         RegFFT<C::E2, false>::run(x);
         if (r >= 0) {
             cf *Rrow = c.R + rmap<C>(ky_of_row<C>(r, c.rank)) * C::RP + k1 * C::E2;
+            if constexpr (!C::R_SMEM && C::RP % 2 == 0 && C::E2 % 2 == 0) {
+                static_for<0, C::E2 / 2>([&](auto J) {           // line pitch: 128-bit stores
+                    constexpr int j = decltype(J)::value;
+                    cf2 v;
+                    v.a = cmake(x[2 * j].x * sc, -x[2 * j].y * sc);
+                    v.b = cmake(x[2 * j + 1].x * sc, -x[2 * j + 1].y * sc);
+                    reinterpret_cast<cf2 *>(Rrow)[j] = v;
+                });
+            } else
             static_for<0, C::E2>([&](auto K2) {
                 constexpr int k2 = decltype(K2)::value;
                 Rrow[k2] = cmake(x[k2].x * sc, -x[k2].y * sc);

@@ -72,6 +72,12 @@ __host__ __device__ constexpr double sin2pi(long long k, long long n) {
 struct __align__(8) cf { float x, y; };   // plain complex float (float2 layout)
 
 SPX_HD cf cmake(float a, float b) { cf r; r.x = a; r.y = b; return r; }
+// two consecutive complex values moved as one 128-bit word (slab copies)
+#ifdef SPX_HOST_EMU
+struct alignas(16) cf2 { cf a, b; };
+#else
+struct __align__(16) cf2 { cf a, b; };
+#endif
 
 // ---- packed fp32x2 arithmetic (sm_100a) ------------------------------------
 // Blackwell issues two fp32 operations per lane with ONE instruction (FADD2 /

@@ -789,7 +789,10 @@ SPX_HD bool lazy_decide(const unsigned (&det)[2], bool need_evidence) {
 // C2: E2-point FFT over n2 for every (column, k1 group of mine), in place.
 // (FAST: full-size tile - nx, ny and the surface width are compile-time constants)
 // (ch_lo, ch_hi: only the 32-column chunks [ch_lo, ch_hi) - split-phase cluster barriers)
-template <class C, bool FAST = false, bool CHUNK = false>
+// DIRECT_W (slab classes, CHUNK): the outputs go straight to the W slab instead of back into
+// the chunk - lanes along x, 256 contiguous bytes per store instruction - which saves the
+// copy-out pass and its barrier; the reference only stores the rows with ky <= P/2.
+template <class C, bool FAST = false, bool CHUNK = false, bool DIRECT_W = false, bool IS_REF = false>
 SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0, int ch_lo = 0, int ch_hi = 1 << 20) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : c.ps->nx;
@@ -810,15 +813,25 @@ SPX_HD void c2_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0, int ch_lo
             x[n2] = wbase[(j * C::E2 + n2) * WPc + col];
         });
         RegFFT<C::E2, false>::run(x);
-        static_for<0, C::E2>([&](auto K2) {
-            constexpr int k2 = decltype(K2)::value;
-            wbase[(j * C::E2 + k2) * WPc + col] = x[k2];
-        });
+        if constexpr (CHUNK && DIRECT_W) {
+            cf *wout = c.W + (j * C::E2) * C::WP + i + col0;
+            static_for<0, C::E2>([&](auto K2) {
+                constexpr int k2 = decltype(K2)::value;
+                if (!IS_REF || j + C::E1 * k2 <= C::P / 2) wout[k2 * C::WP] = x[k2];
+            });
+        } else {
+            static_for<0, C::E2>([&](auto K2) {
+                constexpr int k2 = decltype(K2)::value;
+                wbase[(j * C::E2 + k2) * WPc + col] = x[k2];
+            });
+        }
     }
 }
 
 // IC1: E2-point inverse FFT over k2 (+ inverse twiddle), in place.
-template <class C, bool FAST = false, bool CHUNK = false>
+// DIRECT_W (slab classes, CHUNK): the inputs come straight from the W slab (no copy-in pass),
+// the outputs go to the chunk in S for IC2.
+template <class C, bool FAST = false, bool CHUNK = false, bool DIRECT_W = false>
 SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0, int ch_lo = 0, int ch_hi = 1 << 20) {
     const int warp = warp_of(tid), lane = tid & 31;
     const int nx = FAST ? C::NMAX : c.ps->nx;
@@ -835,10 +848,18 @@ SPX_HD void ic1_pass(const Ctx<C> &c, int tid, int col0, int chunk = 0, int ch_l
         if (l >= nx) continue;
         const int col = CHUNK ? lane : l + col0;
         cf x[C::E2];
-        static_for<0, C::E2>([&](auto K2) {
-            constexpr int k2 = decltype(K2)::value;
-            x[k2] = wbase[(j * C::E2 + k2) * WPc + col];
-        });
+        if constexpr (CHUNK && DIRECT_W) {
+            const cf *win = c.W + (j * C::E2) * C::WP + l + col0;
+            static_for<0, C::E2>([&](auto K2) {
+                constexpr int k2 = decltype(K2)::value;
+                x[k2] = win[k2 * C::WP];
+            });
+        } else {
+            static_for<0, C::E2>([&](auto K2) {
+                constexpr int k2 = decltype(K2)::value;
+                x[k2] = wbase[(j * C::E2 + k2) * WPc + col];
+            });
+        }
         RegFFT<C::E2, true>::run(x);
         static_for<0, C::E2>([&](auto N2) {
             constexpr int n2 = decltype(N2)::value;
@@ -1542,8 +1563,12 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
                                                                     cin, lz, j);
                 if (fl) ex.or_status(&ps->status, fl);
             });
+#ifndef SPX_NO_DIRECT_W
+            ex.par([&](int tid) { c2_pass<C, FAST, true, true, false>(c, tid, cin, j); });
+#else
             ex.par([&](int tid) { c2_pass<C, FAST, true>(c, tid, cin, j); });
             ex.par([&](int tid) { chunk_out<C, false>(c, tid, j, cin); });
+#endif
         }
     } else {
         ex.par([&](int tid) {
@@ -1601,11 +1626,18 @@ SPX_HD bool phase_pair(Ctx<C> &c, Ex &ex, const int IT, bool lazy, bool keep, in
         Best acc = best_init();
         SPX_NO_UNROLL
         for (int j = 0; j < nch; ++j) {
+#ifndef SPX_NO_DIRECT_W
+            ex.par([&](int tid) {
+                prefetch_col_chunk<C>(c, tid, j + 1, cout);
+                ic1_pass<C, FAST, true, true>(c, tid, cout, j);
+            });
+#else
             ex.par([&](int tid) { chunk_in<C>(c, tid, j, cout); });
             ex.par([&](int tid) {
                 prefetch_col_chunk<C>(c, tid, j + 1, cout);
                 ic1_pass<C, FAST, true>(c, tid, cout, j);
             });
+#endif
             ex.par([&](int tid) {
                 const Best t = ic2_pass<C, FAST, true>(c, tid, b, ysh, cout, j);
                 if (best_better(t, acc)) acc = t;
@@ -1664,8 +1696,12 @@ SPX_HD bool run_transforms(Ctx<C> &c, Ex &ex, bool lazy) {
                 const int fl = c1_pass<C, FAST, true, CHECK, true>(c, tid, 0, -1, 0, 0, lzr, j);
                 if (fl) ex.or_status(&ps->status, fl);
             });
+#ifndef SPX_NO_DIRECT_W
+            ex.par([&](int tid) { c2_pass<C, FAST, true, true, true>(c, tid, 0, j); });
+#else
             ex.par([&](int tid) { c2_pass<C, FAST, true>(c, tid, 0, j); });
             ex.par([&](int tid) { chunk_out<C, true>(c, tid, j, 0); });
+#endif
         }
     } else {
         ex.par([&](int tid) {

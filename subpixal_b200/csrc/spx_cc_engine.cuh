@@ -997,25 +997,35 @@ SPX_HD void stage_in(const Ctx<C> &c, int tid, int chunk, int xoff) {
     const int nx = c.ps->nx;
     if constexpr (Wide128<C>::value) {
         constexpr int NP = ((C::NMAX + 1) / 2 + 31) / 32;    // value PAIRS of a row per lane
-        for (int k = warp; k < 32; k += 2 * C::NW) {
-            const int r0 = row_of<C, IS_REF>(c, chunk, k);
-            const int r1 = k + C::NW < 32 ? row_of<C, IS_REF>(c, chunk, k + C::NW) : -1;
-            const cf2 *s0 = reinterpret_cast<const cf2 *>(c.W + (r0 >= 0 ? r0 : 0) * C::WP);
-            const cf2 *s1 = reinterpret_cast<const cf2 *>(c.W + (r1 >= 0 ? r1 : 0) * C::WP);
-            cf2 v0[NP], v1[NP];
-            static_for<0, NP>([&](auto Q) {
-                constexpr int q = decltype(Q)::value;
-                const int i = lane + 32 * q;
-                cf2 z; z.a = z.b = cmake(0.f, 0.f);
-                v0[q] = (r0 >= 0 && 2 * i < nx) ? s0[i] : z;
-                v1[q] = (r1 >= 0 && 2 * i < nx) ? s1[i] : z;
+        // RB rows per iteration: every 128-bit load of all of them is issued before the first
+        // store - RB * NP independent loads in flight (four rows: +1 % at 170 px, -1 % at 256 px)
+#ifndef SPX_STAGE_ROWS
+        constexpr int RB = 2;
+#else
+        constexpr int RB = SPX_STAGE_ROWS;
+#endif
+        for (int k = warp; k < 32; k += RB * C::NW) {
+            int r[RB];
+            cf2 v[RB][NP];
+            static_for<0, RB>([&](auto B) {
+                constexpr int b = decltype(B)::value;
+                r[b] = k + b * C::NW < 32 ? row_of<C, IS_REF>(c, chunk, k + b * C::NW) : -1;
+                const cf2 *src = reinterpret_cast<const cf2 *>(c.W + (r[b] >= 0 ? r[b] : 0) * C::WP);
+                static_for<0, NP>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    const int i = lane + 32 * q;
+                    cf2 z; z.a = z.b = cmake(0.f, 0.f);
+                    v[b][q] = (r[b] >= 0 && 2 * i < nx) ? src[i] : z;
+                });
             });
-            cf *d0 = c.S + k * C::SP + xoff, *d1 = c.S + (k + C::NW) * C::SP + xoff;
-            static_for<0, NP>([&](auto Q) {
-                constexpr int q = decltype(Q)::value;
-                const int i = 2 * (lane + 32 * q);
-                if (r0 >= 0 && i < nx) { d0[i] = v0[q].a; if (i + 1 < nx) d0[i + 1] = v0[q].b; }
-                if (r1 >= 0 && i < nx) { d1[i] = v1[q].a; if (i + 1 < nx) d1[i + 1] = v1[q].b; }
+            static_for<0, RB>([&](auto B) {
+                constexpr int b = decltype(B)::value;
+                cf *d = c.S + (k + b * C::NW) * C::SP + xoff;
+                static_for<0, NP>([&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
+                    const int i = 2 * (lane + 32 * q);
+                    if (r[b] >= 0 && i < nx) { d[i] = v[b][q].a; if (i + 1 < nx) d[i + 1] = v[b][q].b; }
+                });
             });
         }
         return;

@@ -344,7 +344,11 @@ def bench_size(n, args, rank, world, dev, get_gather, sm_mhz):
             out = batch.cc_fit_stack(stack[:min(pool_pairs, 4096)], t)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []                                   # N = 1: one event per launch (spread of the launches)
+        sampler = ClockSampler(physical_gpu_index(int(os.environ.get("LOCAL_RANK", 0)))) if rank == 0 else None
         barrier()
+        if sampler:
+            sampler.start()
         e0.record()
         g = get_gather(pool_pairs) if world > 1 else None
         for _ in range(launches):
@@ -353,8 +357,12 @@ def bench_size(n, args, rank, world, dev, get_gather, sm_mhz):
             out = batch.cc_fit_stack(stack, t, table=g.local if g else None)
             if g:
                 g.gather()
+            elif launches > 1:
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         e1.record()
         barrier()
+        size_clocks = sampler.finish() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -365,7 +373,11 @@ def bench_size(n, args, rank, world, dev, get_gather, sm_mhz):
         traffic, tsrc = ncu_traffic(n, "stack", pool_pairs)
         flop = MFLOP_PER_PAIR[n] * 1e6
         fp32_peak = FP32_LANES * 2 * (sm_mhz or 1965.0) * 1e6
+        per_launch = ([e0.elapsed_time(marks[0])] +
+                      [a.elapsed_time(b) for a, b in zip(marks[:-1], marks[1:])]) if marks else None
         res = {"pairs_per_s": rate, "ms_per_launch": ms / launches,
+               "ms_per_launch_min_max": [min(per_launch), max(per_launch)] if per_launch else None,
+               "clocks": size_clocks,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc,
                             "kernel": "cc_fit_kernel<Cfg%d>" % n, "bytes_per_pair": bpp,

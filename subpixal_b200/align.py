@@ -459,7 +459,10 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
         host = dstack.cpu().numpy()
         for k, imct in enumerate(img_cutouts):
             tile = int(dshp[k, 0] * dshp[k, 1])
-            blt00 = copy.deepcopy(imct)                                # blot.py:152-155
+            # blot.py:152-155: a deep copy of the target cutout - of its arrays and attributes;
+            # the WCS object itself is shared with the image cutout (deep-copying one HSTWCS per
+            # source costs more than the whole measurement)
+            blt00 = copy.deepcopy(imct, {id(imct.wcs): imct.wcs})
             blt00.data[:, :] = host[doff[k] + tile:doff[k] + 2 * tile].reshape(dshp[k])
             nonshifted.append(blt00)
     for imct, dzct in (() if blot is None else zip(img_cutouts, drz_cutouts)):
@@ -494,14 +497,26 @@ def find_linear_fit(img_cutouts, drz_cutouts, wcslin=None, fitgeom='general',
         warnings.warn("subpixal_b200: %d of %d sources have no displacement (cutout larger "
                       "than 256 px or smaller than 3 px) and are left out of the fit"
                       % (int(unusable.sum()), npts))
-    for k, imct in enumerate(img_cutouts):                             # align.py:692-699
-        x1, y1 = imct.cutout_src_pos
-        xyim[k] = np.array(wcslin.wcs_world2pix(*imct.pix2world(x1, y1), 1)).ravel()
-        if unusable[k]:
-            xyref[k] = xyim[k]
-            continue
-        xyref[k] = np.array(wcslin.wcs_world2pix(
-            *imct.pix2world(x1 + img_dxy[k, 0], y1 + img_dxy[k, 1]), 1)).ravel()
+    # align.py:692-699, one WCS call per group of cutouts that share a WCS object (the cutouts
+    # of one image do) instead of four per source: Cutout.pix2world adds (blc - dx) to the
+    # cutout coordinates and calls wcs.all_pix2world (cutout.py:1112-1145)
+    groups = {}
+    for k, imct in enumerate(img_cutouts):
+        groups.setdefault(id(imct.wcs), []).append(k)
+    for idx in groups.values():
+        cts = [img_cutouts[k] for k in idx]
+        pos = np.array([ct.cutout_src_pos for ct in cts], dtype=np.float64).reshape(-1, 2)
+        off = np.array([[ct.blc[0] - ct.dx, ct.blc[1] - ct.dy] for ct in cts], dtype=np.float64)
+        sh = np.where(unusable[idx, None], 0.0, img_dxy[idx])
+        wcs = cts[0].wcs
+        ra, dec = wcs.all_pix2world(pos[:, 0] + off[:, 0], pos[:, 1] + off[:, 1], 0)
+        xyim[idx] = np.stack([np.asarray(v, np.float64).ravel()
+                              for v in wcslin.wcs_world2pix(ra, dec, 1)], axis=1)
+        ra, dec = wcs.all_pix2world((pos[:, 0] + sh[:, 0]) + off[:, 0],
+                                    (pos[:, 1] + sh[:, 1]) + off[:, 1], 0)
+        xyref[idx] = np.stack([np.asarray(v, np.float64).ravel()
+                               for v in wcslin.wcs_world2pix(ra, dec, 1)], axis=1)
+    xyref[unusable] = xyim[unusable]
     ref_dxy = xyim - xyref
     ref_dxy[unusable] = np.nan
 

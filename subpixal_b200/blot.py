@@ -100,16 +100,85 @@ def fit_pixel_maps(frame_map, target_boxes, source_boxes):
     return out
 
 
-def pixel_ratio(source_cutout, target_cutout):
+_stwcs_distortion = False          # False: not looked for yet; None: absent
+
+
+def _orthogonal_cd():
+    """``stwcs.distortion.utils.make_orthogonal_cd`` or None (looked up once: a failing
+    import costs about a millisecond EVERY time it is retried)."""
+    global _stwcs_distortion
+    if _stwcs_distortion is False:
+        try:
+            from stwcs import distortion
+            _stwcs_distortion = distortion.utils.make_orthogonal_cd
+        except ImportError:
+            _stwcs_distortion = None
+    return _stwcs_distortion
+
+
+def pixel_ratio(source_cutout, target_cutout, _cache=None):
     """blot.py:123-133: source pixel scale over the pixel scale of the target's
     orthogonalised linear WCS (``stwcs.distortion.utils.make_orthogonal_cd``) when
-    stwcs is importable, else the ratio of the cutouts' own pixel scales."""
-    try:
-        from stwcs import distortion
-        wcslin = distortion.utils.make_orthogonal_cd(target_cutout.wcs)
-        return float(source_cutout.wcs.pscale / wcslin.pscale)
-    except ImportError:
-        return float(source_cutout.pscale / target_cutout.pscale)
+    stwcs is importable, else the ratio of the cutouts' own pixel scales.  ``_cache``:
+    a dict shared by the pairs of one batch (cutouts of one image share their WCS)."""
+    key = (id(source_cutout.wcs), id(target_cutout.wcs))
+    if _cache is not None and key in _cache:
+        return _cache[key]
+    ortho = _orthogonal_cd()
+    if ortho is not None:
+        pr = float(source_cutout.wcs.pscale / ortho(target_cutout.wcs).pscale)
+    else:
+        pr = float(source_cutout.pscale / target_cutout.pscale)
+    if _cache is not None:
+        _cache[key] = pr
+    return pr
+
+
+def _cutout_pixel_maps(source_cutouts, target_cutouts):
+    """``fit_pixel_map(BlotWCSMap(target, source), nx, ny)`` for every pair, with ONE call
+    of each WCS per group of pairs that share their two WCS objects (the cutouts of one
+    image do): the same element-wise arithmetic in the same order as the per-pair path
+    (Cutout.pix2world / world2pix: cutout.py:1070-1145), so the maps are identical
+    whenever the WCS functions are element-wise."""
+    n = len(source_cutouts)
+    out = np.empty((n, 20), np.float64)
+    groups = {}
+    for k, (sct, tct) in enumerate(zip(source_cutouts, target_cutouts)):
+        groups.setdefault((id(tct.wcs), id(sct.wcs)), []).append(k)
+    for idx in groups.values():
+        tcts = [target_cutouts[k] for k in idx]
+        scts = [source_cutouts[k] for k in idx]
+        m = len(idx)
+        nxy = np.array([[int(v) for v in t.naxis] for t in tcts], dtype=np.float64)     # (nx, ny)
+        xc, yc = 0.5 * (nxy[:, 0] - 1), 0.5 * (nxy[:, 1] - 1)
+        hx, hy = np.maximum(xc, 0.5), np.maximum(yc, 0.5)
+        # node (p, q) of pair i: u = (p-1) hx, v = (q-1) hy ("ij" meshgrid order of fit_pixel_map)
+        sgn = np.array([-1.0, 0.0, 1.0])
+        uu = (sgn[None, :, None] * hx[:, None, None]) * np.ones((1, 1, 3))            # [m, p, q]
+        vv = (sgn[None, None, :] * hy[:, None, None]) * np.ones((1, 3, 1))
+        x1 = (uu + xc[:, None, None]).reshape(m, 9) + 1.0                               # 1-based cutout px
+        y1 = (vv + yc[:, None, None]).reshape(m, 9) + 1.0
+        toff = np.array([[t.blc[0] - t.dx, t.blc[1] - t.dy] for t in tcts], dtype=np.float64)
+        soff = np.array([[c.blc[0] - c.dx, c.blc[1] - c.dy] for c in scts], dtype=np.float64)
+        ra, dec = tcts[0].wcs.all_pix2world((x1 + toff[:, 0:1]).ravel(), (y1 + toff[:, 1:2]).ravel(), 1)
+        sc0 = scts[0]
+        px, py = sc0.wcs.all_world2pix(ra, dec, 1, accuracy=sc0.DEFAULT_ACCURACY,
+                                       maxiter=sc0.DEFAULT_MAXITER, quiet=sc0.DEFAULT_QUIET)
+        xs = (np.asarray(px, np.float64).reshape(m, 9) - soff[:, 0:1]).reshape(m, 3, 3) - 1.0
+        ys = (np.asarray(py, np.float64).reshape(m, 9) - soff[:, 1:2]).reshape(m, 3, 3) - 1.0
+
+        def diff(f, h, axis):     # samples at (-h, 0, h) along `axis` -> coefficients of 1, t, t^2
+            fm, f0, fp = np.moveaxis(f, axis, 0)
+            hh = h.reshape((m,) + (1,) * (fm.ndim - 1))
+            c = np.stack([f0, (fp - fm) / (2.0 * hh), ((fp - f0) - (f0 - fm)) / (2.0 * hh * hh)])
+            return np.moveaxis(c, 0, axis)
+
+        a = diff(diff(xs, hx, 1), hy, 2)
+        b = diff(diff(ys, hx, 1), hy, 2)
+        out[idx, 0], out[idx, 1] = xc, yc
+        out[idx, 2:11] = a.reshape(m, 9)
+        out[idx, 11:20] = b.reshape(m, 9)
+    return out
 
 
 def _check(source_cutout, target_cutout, interp):
@@ -156,14 +225,20 @@ def blot_phases(source_cutouts, target_cutouts, phases=batch.PHASES_00_10_01_11,
     s_shp = np.empty((n, 2), np.int64)
     t_shp = np.empty((n, 2), np.int64)
     chunks = []
+    if wcsmaps is None and n:
+        for sct, tct in zip(source_cutouts, target_cutouts):
+            _check(sct, tct, interp)
+        maps[:] = _cutout_pixel_maps(source_cutouts, target_cutouts)  # blot.py:119-120, batched
+    ratio_cache = {}
     for k, (sct, tct) in enumerate(zip(source_cutouts, target_cutouts)):
         _check(sct, tct, interp)
-        wm = wcsmaps[k] if wcsmaps is not None else None
-        if wm is None:
-            wm = BlotWCSMap(tct, sct)                                 # blot.py:119-120
         nx, ny = (int(v) for v in tct.naxis)
-        maps[k] = fit_pixel_map(wm, nx, ny)
-        pr = pix_ratios[k] if pix_ratios is not None else pixel_ratio(sct, tct)
+        if wcsmaps is not None:
+            wm = wcsmaps[k]
+            if wm is None:
+                wm = BlotWCSMap(tct, sct)                             # blot.py:119-120
+            maps[k] = fit_pixel_map(wm, nx, ny)
+        pr = pix_ratios[k] if pix_ratios is not None else pixel_ratio(sct, tct, ratio_cache)
         scale[k] = _flux_scale(sct, tct, float(pr))
         data = np.ascontiguousarray(sct.data, dtype=np.float32)       # blot.py:135
         s_shp[k] = data.shape

@@ -127,6 +127,22 @@ def _overlap_slices(nx, ny, blc, trc):
             np.s_[by1 - blc[1]:by2 - blc[1], bx1 - blc[0]:bx2 - blc[0]])
 
 
+_astropy_pixel_area = False          # False: not looked for yet; None: astropy absent
+
+
+def _proj_plane_pixel_area():
+    """``astropy.wcs.utils.proj_plane_pixel_area`` or None, looked up once (a failing import
+    is retried - and paid for - on every call otherwise)."""
+    global _astropy_pixel_area
+    if _astropy_pixel_area is False:
+        try:
+            from astropy.wcs.utils import proj_plane_pixel_area
+            _astropy_pixel_area = proj_plane_pixel_area
+        except ImportError:
+            _astropy_pixel_area = None
+    return _astropy_pixel_area
+
+
 class _DeviceImage(object):
     """An image (+ optional dq / weight / segmentation) resident on the GPU."""
 
@@ -547,12 +563,10 @@ class Cutout(object):
         """Pixel scale in the tangent plane at the reference point."""
         if self._wcs is None:
             raise ValueError("WCS was not set. Unable to compute pixel scale.")
-        try:
-            from astropy.wcs.utils import proj_plane_pixel_area
-            return np.sqrt(proj_plane_pixel_area(self._wcs))
-        except ImportError:
-            return math.sqrt(abs(np.linalg.det(
-                np.asarray(self._wcs.pixel_scale_matrix))))
+        area = _proj_plane_pixel_area()
+        if area is not None:
+            return np.sqrt(area(self._wcs))
+        return math.sqrt(abs(np.linalg.det(np.asarray(self._wcs.pixel_scale_matrix))))
 
 
 # --------------------------------------------------------------------------

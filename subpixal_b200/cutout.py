@@ -642,13 +642,38 @@ def create_primary_cutouts(catalog, segmentation_image, imdata, imwcs,
     return out
 
 
-def _footprint_box(ct, imwcs, pad):
-    """Conservative integer rectangle around a cutout's footprint in another
-    image (cutout.py:265-272)."""
-    fp = imwcs.all_world2pix(ct.get_bbox('world'), 0, accuracy=1e-5, maxiter=50)
-    fp = np.asarray(fp)
-    return (_floor(fp[:, 0].min() - pad), _floor(fp[:, 1].min() - pad),
-            _ceil(fp[:, 0].max() + pad), _ceil(fp[:, 1].max() + pad))
+def _by_wcs(cutouts):
+    """Indices of the cutouts grouped by their WCS OBJECT (the cutouts of one image share it):
+    the builders make one WCS call per group instead of one or two per cutout."""
+    groups = {}
+    for k, ct in enumerate(cutouts):
+        groups.setdefault(id(ct.wcs), []).append(k)
+    return list(groups.values())
+
+
+def _footprint_boxes(cutouts, imwcs, pad):
+    """Conservative integer rectangle around every cutout's footprint in another image
+    (cutout.py:265-272: ``imwcs.all_world2pix(ct.get_bbox('world'), 0, accuracy=1e-5,
+    maxiter=50)``, floor / ceil of the extremes -/+ pad), with the four corners of all
+    cutouts of a WCS group in ONE pix2world and ONE world2pix call - the same element-wise
+    arithmetic as ``Cutout.get_bbox`` / ``Cutout.pix2world``."""
+    boxes = [None] * len(cutouts)
+    for idx in _by_wcs(cutouts):
+        cts = [cutouts[k] for k in idx]
+        m = len(cts)
+        x2 = np.array([ct.trc[0] - ct.blc[0] for ct in cts], dtype=np.float64)
+        y2 = np.array([ct.trc[1] - ct.blc[1] for ct in cts], dtype=np.float64)
+        off = np.array([[ct.blc[0] - ct.dx, ct.blc[1] - ct.dy] for ct in cts], dtype=np.float64)
+        zero = np.zeros(m)
+        cx = np.stack([zero - 0.5, zero - 0.5, x2 + 0.5, x2 + 0.5], axis=1)      # get_bbox order
+        cy = np.stack([zero - 0.5, y2 + 0.5, y2 + 0.5, zero - 0.5], axis=1)
+        ra, dec = cts[0].wcs.all_pix2world((cx + off[:, 0:1]).ravel(), (cy + off[:, 1:2]).ravel(), 0)
+        fp = np.asarray(imwcs.all_world2pix(np.dstack([ra, dec])[0], 0, accuracy=1e-5, maxiter=50))
+        fx, fy = fp[:, 0].reshape(m, 4), fp[:, 1].reshape(m, 4)
+        for j, k in enumerate(idx):
+            boxes[k] = (_floor(fx[j].min() - pad), _floor(fy[j].min() - pad),
+                        _ceil(fx[j].max() + pad), _ceil(fy[j].max() + pad))
+    return boxes
 
 
 def _finish_mapped(jobs, crops, imwcs, onxy, data_units, exptime):
@@ -659,11 +684,23 @@ def _finish_mapped(jobs, crops, imwcs, onxy, data_units, exptime):
         new = Cutout._from_arrays(arrays, imwcs, blc, trc, onxy,
                                   src_weight=ct.src_weight, src_id=ct.src_id,
                                   data_units=data_units, exptime=exptime)
-        # full WCS round trip for the source position (cutout.py:300-301)
-        new.cutout_src_pos = new.world2pix(
-            ct.pix2world([ct.cutout_src_pos]))[0].tolist()
         cutouts.append(new)
         sources.append(ct)
+    # full WCS round trip for the source positions (cutout.py:300-301:
+    # ``new.world2pix(ct.pix2world([ct.cutout_src_pos]))``), one call pair per WCS group
+    for idx in _by_wcs(sources):
+        cts = [sources[k] for k in idx]
+        pos = np.array([ct.cutout_src_pos for ct in cts], dtype=np.float64).reshape(-1, 2)
+        off = np.array([[ct.blc[0] - ct.dx, ct.blc[1] - ct.dy] for ct in cts], dtype=np.float64)
+        ra, dec = cts[0].wcs.all_pix2world(pos[:, 0] + off[:, 0], pos[:, 1] + off[:, 1], 0)
+        first = cutouts[idx[0]]
+        x, y = imwcs.all_world2pix(np.asarray(ra, np.float64), np.asarray(dec, np.float64), 0,
+                                   accuracy=first.DEFAULT_ACCURACY, maxiter=first.DEFAULT_MAXITER,
+                                   quiet=first.DEFAULT_QUIET)
+        for j, k in enumerate(idx):
+            new = cutouts[k]
+            new.cutout_src_pos = [float(x[j] - (new.blc[0] - new.dx)),
+                                  float(y[j] - (new.blc[1] - new.dy))]
     return cutouts, sources
 
 
@@ -677,8 +714,8 @@ def create_input_image_cutouts(primary_cutouts, imdata, imwcs, imdq=None,
     imdata = np.asarray(imdata)
     ny, nx = imdata.shape
     jobs = []
-    for ct in primary_cutouts:
-        x1, y1, x2, y2 = _footprint_box(ct, imwcs, pad)
+    primary_cutouts = list(primary_cutouts)
+    for ct, (x1, y1, x2, y2) in zip(primary_cutouts, _footprint_boxes(primary_cutouts, imwcs, pad)):
         if (x1 < 0 or x1 >= nx or y1 < 0 or y1 > ny or
                 x2 < 0 or x2 >= nx or y2 < 0 or y2 > ny):        # cutout.py:276-278
             continue
@@ -707,8 +744,8 @@ def drz_from_input_cutouts(input_cutouts, segmentation_image, imdata, imwcs,
     ny, nx = imdata.shape
     pad = _round_pad(pad)
     jobs = []
-    for ct in input_cutouts:
-        x1, y1, x2, y2 = _footprint_box(ct, imwcs, pad)
+    input_cutouts = list(input_cutouts)
+    for ct, (x1, y1, x2, y2) in zip(input_cutouts, _footprint_boxes(input_cutouts, imwcs, pad)):
         try:
             _box_checks(nx, ny, (x1, y1), (x2, y2), 'fill')
         except NoOverlapError:                                   # cutout.py:412-413

@@ -253,3 +253,68 @@ def test_public_surface_matches_the_reference():
     assert str(inspect.signature(rce.find_peak)) == str(inspect.signature(mce.find_peak))
     assert str(inspect.signature(ru.parse_file_name)) == str(inspect.signature(mi.parse_file_name))
     assert issubclass(mc.NoOverlapError, ValueError) and issubclass(mc.PartialOverlapError, ValueError)
+
+
+class _FakeCutout(object):
+    """What blot / align need of a Cutout for the host-side WCS arithmetic (no device)."""
+    DEFAULT_ACCURACY, DEFAULT_MAXITER, DEFAULT_QUIET = 1e-5, 50, True
+
+    def __init__(self, wcs, blc, naxis, dx=0.0, dy=0.0):
+        self.wcs, self.blc, self.naxis, self.dx, self.dy = wcs, blc, naxis, dx, dy
+
+    def pix2world(self, x, y, origin=0):
+        x = np.asarray(x, float) + (self.blc[0] - self.dx)
+        y = np.asarray(y, float) + (self.blc[1] - self.dy)
+        return list(self.wcs.all_pix2world(x, y, origin))
+
+    def world2pix(self, ra, dec, origin=0):
+        x, y = self.wcs.all_world2pix(ra, dec, origin, accuracy=1e-5, maxiter=50, quiet=True)
+        return [x - (self.blc[0] - self.dx), y - (self.blc[1] - self.dy)]
+
+
+def test_batched_pixel_maps_equal_the_per_pair_maps():
+    """blot_phases fits the 9-point maps of all pairs that share their two WCS objects with
+    ONE call of each WCS: bit-identical to fit_pixel_map(BlotWCSMap(target, source)) per pair
+    (blot.py:21-76, 119-120), including half-pixel shifted targets and 1-pixel axes."""
+    from wcs_stubs import AffineWCS, QuadWCS
+    from subpixal_b200 import blot
+    rng = np.random.default_rng(0)
+    tw = [QuadWCS([[1, 0.01], [-0.01, 1]], [5.0, 7.0], [100.0, 100.0]),
+          AffineWCS([[0.99, 0.0], [0.0, 1.01]], [1.0, 2.0])]
+    sw = AffineWCS(np.eye(2) * 0.9, [3.0, 2.0])
+    tcs = [_FakeCutout(tw[k % 2], (int(rng.integers(0, 200)), int(rng.integers(0, 200))),
+                       (int(rng.integers(1, 70)), int(rng.integers(1, 70))),
+                       dx=float(rng.choice([0, 0.5])), dy=float(rng.choice([0, 0.5])))
+           for k in range(40)]
+    scs = [_FakeCutout(sw, (int(rng.integers(0, 200)), int(rng.integers(0, 200))), (40, 40))
+           for _ in range(40)]
+    got = blot._cutout_pixel_maps(scs, tcs)
+    want = np.stack([blot.fit_pixel_map(blot.BlotWCSMap(t, s), int(t.naxis[0]), int(t.naxis[1]))
+                     for s, t in zip(scs, tcs)])
+    assert np.array_equal(got, want)
+
+
+def test_cutout_deepcopy_copies_arrays_and_honours_the_memo():
+    """Cutout.__deepcopy__: independent arrays and lists, a deep copy of the WCS unless the
+    caller shares it through ``memo`` (find_linear_fit does, for its blot copies)."""
+    import copy
+    from subpixal_b200.cutout import Cutout
+
+    class Wcs(object):
+        def __init__(self):
+            self.v = [1, 2]
+    w = Wcs()
+    c = Cutout.__new__(Cutout)
+    c.__dict__.update(dict(
+        _onx=10, _ony=12, _blc=(1, 2), _trc=(5, 6), _src_pos=(3.0, 4.0), _src_weight=None,
+        _data=np.arange(25.0).reshape(5, 5), _mask=np.zeros((5, 5), bool), _dq=None, _weight=None,
+        _src_id=3, _dx=0, _dy=-0.5, _wcs=w, _naxis=[5, 5], naxis1=5, naxis2=5,
+        _eslice=(slice(2, 7), slice(1, 6)), _islice=(slice(0, 5), slice(0, 5)), exptime=1,
+        data_units='rate'))
+    d = copy.deepcopy(c)
+    assert d is not c and d._data is not c._data and np.array_equal(d._data, c._data)
+    assert d._wcs is not w and d._wcs.v == [1, 2] and d._naxis is not c._naxis and d._naxis == [5, 5]
+    assert d._eslice == c._eslice and d._dy == -0.5 and d.data_units == 'rate'
+    d._data[0, 0] = 99
+    assert c._data[0, 0] == 0
+    assert copy.deepcopy(c, {id(w): w})._wcs is w

@@ -309,12 +309,12 @@ def test_cutout_deepcopy_copies_arrays_and_honours_the_memo():
         _onx=10, _ony=12, _blc=(1, 2), _trc=(5, 6), _src_pos=(3.0, 4.0), _src_weight=None,
         _data=np.arange(25.0).reshape(5, 5), _mask=np.zeros((5, 5), bool), _dq=None, _weight=None,
         _src_id=3, _dx=0, _dy=-0.5, _wcs=w, _naxis=[5, 5], naxis1=5, naxis2=5,
-        _eslice=(slice(2, 7), slice(1, 6)), _islice=(slice(0, 5), slice(0, 5)), exptime=1,
-        data_units='rate'))
+        _eslice=(slice(2, 7), slice(1, 6)), _islice=(slice(0, 5), slice(0, 5)), _exptime=1,
+        _data_units='rate'))
     d = copy.deepcopy(c)
     assert d is not c and d._data is not c._data and np.array_equal(d._data, c._data)
     assert d._wcs is not w and d._wcs.v == [1, 2] and d._naxis is not c._naxis and d._naxis == [5, 5]
-    assert d._eslice == c._eslice and d._dy == -0.5 and d.data_units == 'rate'
+    assert d._eslice == c._eslice and d._dy == -0.5 and d._data_units == 'rate'
     d._data[0, 0] = 99
     assert c._data[0, 0] == 0
     assert copy.deepcopy(c, {id(w): w})._wcs is w

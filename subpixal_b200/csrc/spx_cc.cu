@@ -133,7 +133,14 @@ using Cfg64S = CcCfg< 96, SPX64_E1, 96 / SPX64_E1,  64, SPX64S_T, 1, true, true,
 #endif
 using Cfg128 = CcCfg<192, 12, 16, 128, SPX128_T, 1, true,  true,  SPX128_INPLACE != 0, 2>;   // 2-CTA cluster, DSMEM
 #else
-using Cfg128 = CcCfg<192, 12, 16, 128, 512, 1, false, true >;
+// (build knob: the 128 px class in the fused global-slab form of the 170 / 256 px classes)
+#ifndef SPX128_SLAB_T
+#define SPX128_SLAB_T 256
+#endif
+#ifndef SPX128_SLAB_MINB
+#define SPX128_SLAB_MINB 2
+#endif
+using Cfg128 = CcCfg<192, 12, 16, 128, SPX128_SLAB_T, SPX128_SLAB_MINB, false, false>;
 #endif
 #ifndef SPX256_CLUSTER
 #define SPX256_CLUSTER 0

@@ -176,6 +176,27 @@ def _pinned_pair(device):
     return st["bufs"], st["stream"]
 
 
+READERS = max(2, min(8, (os.cpu_count() or 4) // 2))     # file-reader threads per staging chunk
+_reader_pool = None
+
+
+def _readers():
+    global _reader_pool
+    if _reader_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _reader_pool = ThreadPoolExecutor(max_workers=READERS, thread_name_prefix="spx-fits")
+    return _reader_pool
+
+
+def _pread_into(fd, view, offset, path):
+    got = 0
+    while got < len(view):
+        r = os.preadv(fd, [view[got:]], offset + got)
+        if not r:
+            raise IOError("%s: unexpected end of file" % path)
+        got += r
+
+
 def release_staging():
     """Free the pinned staging buffers (2 x 32 MiB per device)."""
     _staging.clear()
@@ -295,25 +316,29 @@ class FitsFile(object):
         bufs, side = _pinned_pair(device)
         cur = torch.cuda.current_stream(device)
         side.wait_stream(cur)                              # raw is allocated on `cur`
-        with open(self.path, 'rb', buffering=0) as f:
-            f.seek(hdu.data_offset)
+        fd = os.open(self.path, os.O_RDONLY)
+        try:
             done, k = 0, 0
             while done < nbytes:
                 pin, ev = bufs[k & 1]
                 ev.synchronize()                           # its previous upload has left the buffer
                 want = min(_CHUNK, nbytes - done)
                 view = memoryview(pin.numpy())[:want]
-                got = 0
-                while got < want:
-                    r = f.readinto(view[got:])
-                    if not r:
-                        raise IOError("%s: unexpected end of file" % self.path)
-                    got += r
+                # the chunk is read by READERS threads at once (pread releases the GIL; one
+                # thread copies out of the page cache at about 6 GB/s, a PCIe link takes 50)
+                part = -(-want // READERS // 4096) * 4096
+                jobs = [_readers().submit(_pread_into, fd, view[a:min(a + part, want)],
+                                          hdu.data_offset + done + a, self.path)
+                        for a in range(0, want, part)]
+                for j in jobs:
+                    j.result()
                 with torch.cuda.stream(side):
                     raw[done:done + want].copy_(pin[:want], non_blocking=True)
                     ev.record(side)
                 done += want
                 k += 1
+        finally:
+            os.close(fd)
         cur.wait_stream(side)
         raw.record_stream(side)
         return raw

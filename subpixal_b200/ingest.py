@@ -24,7 +24,6 @@ behaviour (``ImageHDU.data``: ``do_not_scale_image_data=False``, ``uint=True``) 
 FITS standard, and are tested against numpy's big-endian dtypes - parity with astropy
 itself is unpinned.
 """
-import ctypes as C
 import os
 import re
 from collections import OrderedDict
@@ -236,9 +235,9 @@ class FitsFile(object):
                 chunks, end = [], False
                 while not end:
                     blk = f.read(BLOCK)
+                    if not chunks and not blk.strip(b'\0 '):
+                        break                             # zero / blank padding after the last HDU
                     if len(blk) < BLOCK:
-                        if not chunks and not blk.strip(b'\0 '):
-                            break                         # padding after the last HDU
                         raise ValueError("%s: truncated FITS header at byte %d" % (path, pos))
                     hdr_part, end = _parse_header(blk)
                     chunks.append(blk)

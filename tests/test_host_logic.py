@@ -323,10 +323,10 @@ def test_cutout_deepcopy_copies_arrays_and_honours_the_memo():
 def test_every_python_file_compiles():
     """bench.py, __graft_entry__.py, the package, the oracle and every developer tool parse."""
     import glob
-    import py_compile
     files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
     for sub in ("subpixal_b200", "oracle", "tools", "tests", os.path.join("tests", "golden")):
         files += glob.glob(os.path.join(ROOT, sub, "*.py"))
     assert len(files) > 40
     for f in files:
-        py_compile.compile(f, doraise=True, cfile=os.devnull)
+        with open(f) as fh:
+            compile(fh.read(), f, "exec")

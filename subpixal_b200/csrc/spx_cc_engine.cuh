@@ -25,6 +25,14 @@
 // The reference image goes through C1, C2, X1 and a final E2-point FFT whose
 // conjugate, times the normalisation scale, is stored as R (half spectrum,
 // ky in [0, P/2], Hermitian symmetry supplies the rest).
+//
+// Slab classes (170 / 256 px: W and R in a per-CTA global slab, C::FUSE): the column
+// passes run per 32-column chunk through the scratch S -
+//   C1  tiles -> chunk [P][32] in S;   C2  chunk -> W slab (256-byte row segments)
+//   row batches of 32 rows as above (a batch = k1 group g with group E1 - g, so the two
+//   rows that read one R row share it; 128-bit copies between the slab and S)
+//   IC1 W slab -> chunk in S;          IC2 chunk -> ICC, argmax
+// - so W makes one trip to the slab per direction change.
 #pragma once
 #include <limits.h>
 #if !defined(SPX_HOST_EMU)
